@@ -1,0 +1,137 @@
+/* msd_b200.h -- C ABI of libmsd_b200.so: the B200 (sm_100a) implementation of the DDPM
+ * sampling hot path of magenta/music-spectrogram-diffusion.
+ *
+ * The reference has no FFI/plugin layer (it is pure Python on JAX/XLA); the drop-in boundary
+ * is the Python protocol of `inference.InferenceModel` (music_spectrogram_diffusion/
+ * inference.py:68-203).  These entry points are what a binding for that protocol binds; each
+ * one names the reference code it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions: every function returns 0 on success, a negative code on failure
+ * (-1 bad argument / unsupported configuration, -2 CUDA error, -3 missing weight);
+ * `msd_last_error()` returns a thread-local message.  Pointers documented "device" are CUDA
+ * device pointers owned by the caller; "host" are ordinary host pointers.  A context is bound
+ * to one GPU and one stream at a time and is not thread-safe.  `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).
+ */
+#ifndef MSD_B200_H_
+#define MSD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSD_B200_ABI_VERSION 1
+
+typedef struct msd_ctx msd_ctx;
+
+/* Static model + sampler description.
+ * Mirrors network.T5Config (models/diffusion/network.py:54-72), the task feature lengths
+ * (gin/tasks/mt3/context_mega.gin:5), diffusion_utils.DiffusionConfig/SamplerConfig
+ * (models/diffusion/diffusion_utils.py:25-59) and the MelGAN codec constants
+ * (audio_codecs.py:204-213). */
+typedef struct msd_config {
+  int32_t vocab_size;            /* T5Config.vocab_size (1536 for the mt3 vocabulary) */
+  int32_t emb_dim;               /* multiple of 128, <= 1024 */
+  int32_t num_heads;
+  int32_t head_dim;              /* must be 64 */
+  int32_t num_encoder_layers;
+  int32_t num_decoder_layers;
+  int32_t mlp_dim;               /* gated ('gelu','linear') MLP; multiple of 64 */
+  int32_t inputs_length;         /* token positions, multiple of 128 */
+  int32_t targets_length;        /* mel frames per segment, multiple of 128 */
+  int32_t context_length;        /* context frames, multiple of 128 */
+  int32_t n_dims;                /* mel bins, must be 128 */
+  int32_t num_steps;             /* sampler schedule num_steps */
+  int32_t max_batch;             /* segments per call (B) */
+  int32_t sampler;               /* 0 = ddpm, 1 = ddim */
+  int32_t logvar_type;           /* 0 = large, 1 = small (ddpm only) */
+  int32_t clip_x0;               /* SamplerConfig.clip_x0 */
+  int32_t context_positions;     /* 0 = regular, 1 = terminal_relative */
+  float max_decoder_noise_time;  /* T5Config.max_decoder_noise_time (2e4) */
+  float eval_condition_weight;   /* classifier-free guidance weight; 1 disables the 2nd pass */
+  float feature_min;             /* codec min_value (log 1e-5) */
+  float feature_max;             /* codec max_value (4.0) */
+} msd_config;
+
+/* A named fp32 parameter in the reference's own layout (flax tree path joined by '/',
+ * kernels [in, out]); see SURVEY.md App. B. */
+typedef struct msd_tensor {
+  const char* name;
+  const float* data; /* host pointer */
+  int32_t ndim;
+  int64_t shape[4];
+} msd_tensor;
+
+const char* msd_last_error(void);
+int msd_abi_version(void);
+
+/* Replaces InferenceModel.__init__'s model construction (inference.py:71-111). */
+int msd_create(const msd_config* cfg, int device, msd_ctx** out);
+void msd_destroy(msd_ctx* ctx);
+
+/* Replaces InferenceModel._restore_from_checkpoint (inference.py:159-176): takes the fp32
+ * parameter tree, repacks it into the kernel layouts (bf16 [out, in], fused QKV / gated-MLP /
+ * split-precision projections) and tabulates the timestep conditioning for all num_steps
+ * (network.py:377-394 + layers.py:652-666: FiLM scale|bias for every (step, layer)). */
+int msd_load_weights(msd_ctx* ctx, const msd_tensor* tensors, int32_t n);
+
+/* Replaces ContextDiffusionModel.predict_batch_with_aux's scale_features + module.encode
+ * (models/diffusion/models.py:361-371; network.py:537-559) and additionally projects the
+ * concatenated encodings to every decoder layer's cross-attention K/V once (network.py:217-230
+ * is loop-invariant).  tokens [B, inputs_length] int32, ctx_features [B, context_length,
+ * n_dims] f32 in codec feature units, ctx_mask [B, context_length] int32: device pointers. */
+int msd_encode(msd_ctx* ctx, const int32_t* tokens, const float* ctx_features,
+               const int32_t* ctx_mask, int32_t batch, void* stream);
+
+/* Replaces diffusion_utils.eval_scan + scale_to_features (diffusion_utils.py:456-476;
+ * models.py:393-395) for the batch passed to the preceding msd_encode.
+ * init_z  [B, targets_length, n_dims] f32 device, or NULL -> Philox N(0,1) from `seed`.
+ * noise   [num_steps, B, targets_length, n_dims] f32 device (noise[i] is used at step i),
+ *         or NULL -> Philox from `seed`.
+ * mel_out [B, targets_length, n_dims] f32 device, codec feature units. */
+int msd_sample(msd_ctx* ctx, const float* init_z, const float* noise, uint64_t seed,
+               float* mel_out, void* stream);
+
+/* Test hook == module.decode (network.py:561-573) at diffusion step `step_i`
+ * (time = (step_i + 1) / num_steps): z [B, targets_length, n_dims] f32 device ->
+ * eps_out [B, ...] f32 device.  conditioned = 0 multiplies encodings and masks by 0
+ * (models.py:376-377). */
+int msd_decode_eps(msd_ctx* ctx, const float* z, int32_t step_i, int32_t conditioned,
+                   float* eps_out, void* stream);
+
+/* Test hook: copies the encoder outputs of the last msd_encode as bf16-rounded f32:
+ * enc_out [B, inputs_length + context_length, emb_dim] device f32. */
+int msd_get_encodings(msd_ctx* ctx, float* enc_out, void* stream);
+
+/* Host copy of the per-step sampler scalars [num_steps][8]:
+ * x0_scale, eps_scale, c_z, c_x0, sigma, is_last, logsnr_t, logsnr_s. */
+int msd_get_step_table(msd_ctx* ctx, float* table_host);
+
+/* Kernel launches issued so far by this library in this process (graph replays count their
+ * kernel nodes). */
+uint64_t msd_launch_count(void);
+
+/* ---- operator-level entry points (unit parity against msd/layers.py) ------------------- */
+
+/* DenseGeneral (layers.py:397-442): out[M,N] f32 = A[M,K] * W, with A given as bf16-rounded
+ * f32 [M,K] device and W as f32 [K,N] host-layout device pointer (packed internally). */
+int msd_op_dense(const float* a, const float* w, int32_t M, int32_t N, int32_t K, float* out,
+                 void* stream);
+
+/* dot_product_attention (layers.py:109-181) for head_dim 64 with a key-padding mask:
+ * q [nb, Lq, heads*64], k/v [nb, Lk, heads*64] f32 device, key_mask [nb, Lk] int32 or NULL,
+ * out [nb, Lq, heads*64] f32 device. */
+int msd_op_attention(const float* q, const float* k, const float* v, const int32_t* key_mask,
+                     int32_t nb, int32_t heads, int32_t Lq, int32_t Lk, float* out, void* stream);
+
+/* LayerNorm (layers.py:632-649) followed by optional FiLM (layers.py:652-666) with explicit
+ * scale|bias vector film [2*d] (NULL = none): out f32 (bf16-rounded) [rows, d]. */
+int msd_op_rmsnorm_film(const float* x, const float* gamma, const float* film, int32_t rows,
+                        int32_t d, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSD_B200_H_ */

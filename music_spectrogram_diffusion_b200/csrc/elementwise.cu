@@ -1,0 +1,513 @@
+// Row-wise / element-wise kernels of the DDPM hot path (HBM-bound; vectorised, coalesced):
+//   rmsnorm(+FiLM)   msd/layers.py:632-649 (T5 RMS norm), 652-666 (FiLM x*(1+s)+b)
+//   sampler step     msd/models/diffusion/diffusion_utils.py:398-453, 382-395, 120-163, 215-222
+//   token embedding  msd/layers.py:556-559 + network.py:278-287
+//   feature scaling  msd/audio_codecs.py:166-183
+//   masks            msd/models/diffusion/network.py:28-51, 546; msd/layers.py:341-348
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msd {
+
+unsigned long long g_launch_count = 0;
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// ---------------------------------------------------------------------------
+// RMSNorm (+FiLM) : one warp per row, row kept in registers, bf16 output
+// ---------------------------------------------------------------------------
+struct NormDev {
+  const float* x;
+  const float* gamma;
+  bf16* out;
+  const float* film;
+  const int* step;
+  long long film_step_stride, film_offset;
+  int rows, d, ldo, split3;
+  int src_len, dst_len, dst_off;  // row remap when src_len > 0
+};
+
+constexpr int NORM_MAX_ITERS = 8;  // d <= 1024
+
+__global__ void __launch_bounds__(256) rmsnorm_film_kernel(const NormDev p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.rows) return;
+  const int iters = p.d >> 7;  // float4 per lane
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(warp) * p.d);
+  float4 v[NORM_MAX_ITERS];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAX_ITERS; ++i) {
+    if (i < iters) {
+      v[i] = xr[i * 32 + lane];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss / static_cast<float>(p.d) + 1e-6f);
+  const float* fs = nullptr;
+  const float* fb = nullptr;
+  if (p.film != nullptr) {
+    const long long base = static_cast<long long>(*p.step) * p.film_step_stride + p.film_offset;
+    fs = p.film + base;
+    fb = fs + p.d;
+  }
+  int orow = warp;
+  if (p.src_len > 0) {
+    const int b = warp / p.src_len;
+    orow = b * p.dst_len + p.dst_off + (warp - b * p.src_len);
+  }
+  bf16* o = p.out + static_cast<size_t>(orow) * p.ldo;
+#pragma unroll
+  for (int i = 0; i < NORM_MAX_ITERS; ++i) {
+    if (i < iters) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+      float y0 = v[i].x * inv * g.x, y1 = v[i].y * inv * g.y;
+      float y2 = v[i].z * inv * g.z, y3 = v[i].w * inv * g.w;
+      if (fs != nullptr) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(fs + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(fb + c));
+        y0 = y0 * (s.x + 1.0f) + bb.x; y1 = y1 * (s.y + 1.0f) + bb.y;
+        y2 = y2 * (s.z + 1.0f) + bb.z; y3 = y3 * (s.w + 1.0f) + bb.w;
+      }
+      if (!p.split3) {
+        uint2 u;
+        u.x = pack_bf16(y0, y1);
+        u.y = pack_bf16(y2, y3);
+        *reinterpret_cast<uint2*>(o + c) = u;
+      } else {
+        bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(y0, h0, l0); split_bf16(y1, h1, l1);
+        split_bf16(y2, h2, l2); split_bf16(y3, h3, l3);
+        __nv_bfloat162 a = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
+        __nv_bfloat162 c0 = __halves2bfloat162(l0, l1), c1 = __halves2bfloat162(l2, l3);
+        uint2 uh, ul;
+        uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b2);
+        ul.x = *reinterpret_cast<uint32_t*>(&c0); ul.y = *reinterpret_cast<uint32_t*>(&c1);
+        *reinterpret_cast<uint2*>(o + c) = uh;              // hi
+        *reinterpret_cast<uint2*>(o + p.d + c) = ul;        // lo
+        *reinterpret_cast<uint2*>(o + 2 * p.d + c) = uh;    // hi
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (perf-mode noise; parity runs inject noise instead)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32_t stream,
+                                                 unsigned long long idx4) {
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32), stream, 0x6d7364u,
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const float s = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = (static_cast<float>(r[0]) + 0.5f) * s, u1 = (static_cast<float>(r[1]) + 0.5f) * s;
+  const float u2 = (static_cast<float>(r[2]) + 0.5f) * s, u3 = (static_cast<float>(r[3]) + 0.5f) * s;
+  const float ra = sqrtf(-2.0f * logf(fminf(fmaxf(u0, 1e-12f), 1.0f)));
+  const float rb = sqrtf(-2.0f * logf(fminf(fmaxf(u2, 1e-12f), 1.0f)));
+  float sa, ca, sb, cb;
+  sincospif(2.0f * u1, &sa, &ca);
+  sincospif(2.0f * u3, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+
+__device__ __forceinline__ void store_split4(bf16* zs, long long idx, int n_dims, float4 v) {
+  const long long row = idx / n_dims;
+  const int col = static_cast<int>(idx - row * n_dims);
+  bf16* o = zs + row * (3LL * n_dims) + col;
+  bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+  __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+  __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
+  uint2 uh, ul;
+  uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b);
+  ul.x = *reinterpret_cast<uint32_t*>(&c); ul.y = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint2*>(o) = uh;
+  *reinterpret_cast<uint2*>(o + n_dims) = ul;
+  *reinterpret_cast<uint2*>(o + 2 * n_dims) = uh;
+}
+
+// ---------------------------------------------------------------------------
+// One reverse-diffusion update (CFG combine + x0 + clip + DDPM/DDIM mean + noise)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) {
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long idx = i4 * 4;
+  if (idx >= a.n) return;
+  const int step = *a.step;
+  const float* cf = a.coef + static_cast<size_t>(step) * 8;
+  const float x0_scale = cf[0], eps_scale = cf[1], c_z = cf[2], c_x0 = cf[3], sigma = cf[4];
+  const bool last = cf[5] != 0.f;
+  const float4 z = *reinterpret_cast<const float4*>(a.z + idx);
+  float4 e = *reinterpret_cast<const float4*>(a.eps + idx);
+  if (a.passes == 2) {
+    const float4 eu = *reinterpret_cast<const float4*>(a.eps + a.n + idx);
+    const float w = a.cond_weight, wu = 1.0f - a.cond_weight;
+    e.x = w * e.x + wu * eu.x; e.y = w * e.y + wu * eu.y;
+    e.z = w * e.z + wu * eu.z; e.w = w * e.w + wu * eu.w;
+  }
+  float4 x0;
+  x0.x = x0_scale * (z.x - e.x * eps_scale); x0.y = x0_scale * (z.y - e.y * eps_scale);
+  x0.z = x0_scale * (z.z - e.z * eps_scale); x0.w = x0_scale * (z.w - e.w * eps_scale);
+  if (a.clip_x0) {
+    x0.x = fminf(fmaxf(x0.x, -1.f), 1.f); x0.y = fminf(fmaxf(x0.y, -1.f), 1.f);
+    x0.z = fminf(fmaxf(x0.z, -1.f), 1.f); x0.w = fminf(fmaxf(x0.w, -1.f), 1.f);
+  }
+  float4 zn;
+  if (last) {
+    zn = x0;
+  } else {
+    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sigma != 0.f) {
+      if (a.noise != nullptr) {
+        nz = *reinterpret_cast<const float4*>(a.noise + static_cast<size_t>(step) * a.n + idx);
+      } else {
+        nz = philox_normal4(a.seed, static_cast<uint32_t>(step) + 1u,
+                            static_cast<unsigned long long>(i4));
+      }
+    }
+    zn.x = c_z * z.x + c_x0 * x0.x + sigma * nz.x; zn.y = c_z * z.y + c_x0 * x0.y + sigma * nz.y;
+    zn.z = c_z * z.z + c_x0 * x0.z + sigma * nz.z; zn.w = c_z * z.w + c_x0 * x0.w + sigma * nz.w;
+  }
+  *reinterpret_cast<float4*>(a.z + idx) = zn;
+  store_split4(a.z_split, idx, a.n_dims, zn);
+  if (last && a.mel_out != nullptr) {
+    // scale_to_features, msd/audio_codecs.py:176-183 with input_range (-1, 1)
+    const float span = a.feat_max - a.feat_min;
+    float4 f;
+    f.x = (zn.x + 1.f) * 0.5f * span + a.feat_min; f.y = (zn.y + 1.f) * 0.5f * span + a.feat_min;
+    f.z = (zn.z + 1.f) * 0.5f * span + a.feat_min; f.w = (zn.w + 1.f) * 0.5f * span + a.feat_min;
+    *reinterpret_cast<float4*>(a.mel_out + idx) = f;
+  }
+}
+
+__global__ void step_advance_kernel(int* step) { *step -= 1; }
+
+__global__ void __launch_bounds__(256)
+init_z_kernel(const float* init_z, float* z, bf16* zs, long long n, int n_dims,
+              unsigned long long seed) {
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long idx = i4 * 4;
+  if (idx >= n) return;
+  float4 v;
+  if (init_z != nullptr) v = *reinterpret_cast<const float4*>(init_z + idx);
+  else v = philox_normal4(seed, 0u, static_cast<unsigned long long>(i4));
+  *reinterpret_cast<float4*>(z + idx) = v;
+  store_split4(zs, idx, n_dims, v);
+}
+
+// ---------------------------------------------------------------------------
+// Encoder front ends
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const int* tokens, const float* emb, const float* pos, float* x, int rows,
+                    int T, int d, int vocab) {
+  const int d4 = d >> 2;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(rows) * d4) return;
+  const int row = static_cast<int>(gid / d4), c = static_cast<int>(gid - static_cast<long long>(row) * d4);
+  int tok = tokens[row];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  const int t = row % T;
+  const float4 e = __ldg(reinterpret_cast<const float4*>(emb + static_cast<size_t>(tok) * d) + c);
+  const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * d) + c);
+  reinterpret_cast<float4*>(x + static_cast<size_t>(row) * d)[c] =
+      make_float4(e.x + pp.x, e.y + pp.y, e.z + pp.z, e.w + pp.w);
+}
+
+__global__ void __launch_bounds__(256)
+scale_split_kernel(const float* feat, bf16* out, long long n, int n_dims, float fmin, float fmax) {
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long idx = i4 * 4;
+  if (idx >= n) return;
+  float4 f = *reinterpret_cast<const float4*>(feat + idx);
+  // scale_features(clip=True), msd/audio_codecs.py:166-174 with output_range (-1, 1)
+  const float inv = 1.0f / (fmax - fmin);
+  f.x = (fminf(fmaxf(f.x, fmin), fmax) - fmin) * inv * 2.0f - 1.0f;
+  f.y = (fminf(fmaxf(f.y, fmin), fmax) - fmin) * inv * 2.0f - 1.0f;
+  f.z = (fminf(fmaxf(f.z, fmin), fmax) - fmin) * inv * 2.0f - 1.0f;
+  f.w = (fminf(fmaxf(f.w, fmin), fmax) - fmin) * inv * 2.0f - 1.0f;
+  store_split4(out, idx, n_dims, f);
+}
+
+// One block per batch row: key-mask bit words for [tokens | context] and the
+// terminal-relative roll amount (= get_sequence_length of the context mask).
+__global__ void __launch_bounds__(256)
+build_masks_kernel(const int* tokens, const int* ctx_mask, int T, int C, uint32_t* bits,
+                   int* ctx_seq_len, int terminal_relative) {
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int words_t = T >> 5, words_c = C >> 5;
+  uint32_t* brow = bits + static_cast<size_t>(b) * (words_t + words_c);
+  __shared__ int first_zero;
+  if (threadIdx.x == 0) first_zero = C;
+  __syncthreads();
+  for (int w = warp; w < words_t; w += nw) {
+    const uint32_t m = __ballot_sync(0xffffffffu, tokens[static_cast<size_t>(b) * T + w * 32 + lane] > 0);
+    if (lane == 0) brow[w] = m;
+  }
+  for (int w = warp; w < words_c; w += nw) {
+    const int v = ctx_mask[static_cast<size_t>(b) * C + w * 32 + lane];
+    const uint32_t m = __ballot_sync(0xffffffffu, v > 0);
+    const uint32_t z = __ballot_sync(0xffffffffu, v == 0);
+    if (lane == 0) {
+      brow[words_t + w] = m;
+      if (z) atomicMin(&first_zero, w * 32 + __ffs(z) - 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // network.py:28-39: first zero index, or the full length when there is no zero.
+    int len = first_zero;  // == C when no zero was found
+    ctx_seq_len[b] = terminal_relative ? (len % C) : 0;  // roll by C == roll by 0
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Load-time: weight packing and fp32 SIMT GEMM
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* W, int K, int N, bf16* dst, int ldd, int n_off, int k_off,
+                   int part) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(K) * N) return;
+  const int n = static_cast<int>(gid / K), k = static_cast<int>(gid - static_cast<long long>(n) * K);
+  const float w = W[static_cast<size_t>(k) * N + n];
+  bf16 hi, lo;
+  split_bf16(w, hi, lo);
+  dst[static_cast<size_t>(n_off + n) * ldd + k_off + k] = part ? lo : hi;
+}
+
+__global__ void __launch_bounds__(256)
+pack_gated_kernel(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= 2LL * F * K) return;
+  const int r = static_cast<int>(gid / K), k = static_cast<int>(gid - static_cast<long long>(r) * K);
+  const int g = r >> 6, j = r & 63;
+  const float* W = (j < 32) ? W0 : W1;
+  const int col = g * 32 + (j & 31);
+  dst[static_cast<size_t>(r) * ldd + k] = __float2bfloat16_rn(W[static_cast<size_t>(k) * F + col]);
+}
+
+constexpr int SG_T = 64, SG_K = 16;
+__global__ void __launch_bounds__(256)
+sgemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                 int ldc, int M, int N, int K, int act) {
+  __shared__ float sA[SG_K][SG_T + 1];
+  __shared__ float sB[SG_K][SG_T + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += SG_K) {
+    for (int e = threadIdx.x; e < SG_T * SG_K; e += 256) {
+      const int am = e / SG_K, ak = e % SG_K;
+      const int gm = m0 + am, gk = k0 + ak;
+      sA[ak][am] = (gm < M && gk < K) ? A[static_cast<size_t>(gm) * K + gk] : 0.f;
+      const int bk = e / SG_T, bn = e % SG_T;
+      const int gn = n0 + bn, gk2 = k0 + bk;
+      sB[bk][bn] = (gn < N && gk2 < K) ? B[static_cast<size_t>(gk2) * N + gn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_K; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) {
+        float v = acc[i][j];
+        if (act == 1) v = v / (1.0f + expf(-v));  // swish = x * sigmoid(x)
+        C[static_cast<size_t>(gm) * ldc + gn] = v;
+      }
+    }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* s, bf16* d, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16* s, float* d, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __bfloat162float(s[i]);
+}
+__global__ void __launch_bounds__(256)
+mask_bits_kernel(const int* mask, long long words, uint32_t* bits) {
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= words) return;
+  const uint32_t m = __ballot_sync(0xffffffffu, mask[w * 32 + lane] > 0);
+  if (lane == 0) bits[w] = m;
+}
+
+inline int blocks_for(long long n, int per_block) {
+  return static_cast<int>((n + per_block - 1) / per_block);
+}
+
+}  // namespace
+
+int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* out, int ldo,
+                   const float* film, const int* step, long long film_step_stride,
+                   long long film_offset, int split3, cudaStream_t stream) {
+  MSD_REQUIRE(d % 128 == 0 && d <= 128 * NORM_MAX_ITERS, "rmsnorm: d=%d must be k*128 <= 1024", d);
+  NormDev p;
+  p.x = x; p.gamma = gamma; p.out = out; p.film = film; p.step = step;
+  p.film_step_stride = film_step_stride; p.film_offset = film_offset;
+  p.rows = rows; p.d = d; p.ldo = ldo; p.split3 = split3;
+  p.src_len = 0; p.dst_len = 0; p.dst_off = 0;
+  rmsnorm_film_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(p);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src_len, int d,
+                              bf16* out, int dst_len, int dst_off, cudaStream_t stream) {
+  MSD_REQUIRE(d % 128 == 0 && d <= 128 * NORM_MAX_ITERS, "rmsnorm: d=%d must be k*128 <= 1024", d);
+  NormDev p;
+  p.x = x; p.gamma = gamma; p.out = out; p.film = nullptr; p.step = nullptr;
+  p.film_step_stride = 0; p.film_offset = 0;
+  p.rows = B * src_len; p.d = d; p.ldo = d; p.split3 = 0;
+  p.src_len = src_len; p.dst_len = dst_len; p.dst_off = dst_off;
+  rmsnorm_film_kernel<<<blocks_for(p.rows, 8), 256, 0, stream>>>(p);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream) {
+  MSD_REQUIRE(a.n % 4 == 0 && a.n_dims % 4 == 0, "sampler: sizes must be multiples of 4");
+  sampler_step_kernel<<<blocks_for(a.n / 4, 256), 256, 0, stream>>>(a);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_step_advance(int* step, cudaStream_t stream) {
+  step_advance_kernel<<<1, 1, 0, stream>>>(step);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_init_z(const float* init_z, float* z, bf16* z_split, long long n, int n_dims,
+                  unsigned long long seed, cudaStream_t stream) {
+  init_z_kernel<<<blocks_for(n / 4, 256), 256, 0, stream>>>(init_z, z, z_split, n, n_dims, seed);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_embed_tokens(const int* tokens, const float* emb, const float* pos, float* x, int B,
+                        int T, int d, int vocab, cudaStream_t stream) {
+  const long long n = static_cast<long long>(B) * T * (d / 4);
+  embed_tokens_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(tokens, emb, pos, x, B * T, T, d,
+                                                              vocab);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_scale_split(const float* feat, bf16* out_split, long long rows, int n_dims, float fmin,
+                       float fmax, cudaStream_t stream) {
+  const long long n = rows * n_dims;
+  scale_split_kernel<<<blocks_for(n / 4, 256), 256, 0, stream>>>(feat, out_split, n, n_dims, fmin,
+                                                                 fmax);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_build_masks(const int* tokens, const int* ctx_mask, int B, int T, int C, uint32_t* bits,
+                       int* ctx_seq_len, int terminal_relative, cudaStream_t stream) {
+  MSD_REQUIRE(T % 128 == 0 && C % 128 == 0, "masks: lengths must be multiples of 128");
+  build_masks_kernel<<<B, 256, 0, stream>>>(tokens, ctx_mask, T, C, bits, ctx_seq_len,
+                                            terminal_relative);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_pack_weight(const float* W, int K, int N, bf16* dst, int ldd, int n_off, int k_off,
+                       int part, cudaStream_t stream) {
+  pack_weight_kernel<<<blocks_for(static_cast<long long>(K) * N, 256), 256, 0, stream>>>(
+      W, K, N, dst, ldd, n_off, k_off, part);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_gated(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd,
+                      cudaStream_t stream) {
+  MSD_REQUIRE(F % 32 == 0, "pack_gated: F must be a multiple of 32");
+  pack_gated_kernel<<<blocks_for(2LL * F * K, 256), 256, 0, stream>>>(W0, W1, K, F, dst, ldd);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t stream) {
+  f32_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(src, dst, n);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t stream) {
+  bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(src, dst, n);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_mask_bits(const int* mask, int nb, int L, uint32_t* bits, cudaStream_t stream) {
+  MSD_REQUIRE(L % 128 == 0, "mask_bits: L must be a multiple of 128");
+  const long long words = static_cast<long long>(nb) * (L / 32);
+  mask_bits_kernel<<<blocks_for(words * 32, 256), 256, 0, stream>>>(mask, words, bits);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_sgemm_f32(const float* A, const float* B, float* C, int ldc, int M, int N, int K,
+                     int act, cudaStream_t stream) {
+  dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T);
+  sgemm_f32_kernel<<<grid, 256, 0, stream>>>(A, B, C, ldc, M, N, K, act);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace msd

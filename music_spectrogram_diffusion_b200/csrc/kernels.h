@@ -1,0 +1,143 @@
+// Host-side launcher prototypes for the sm_100a kernels (internal to libmsd_b200.so).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msd {
+
+typedef __nv_bfloat16 bf16;
+
+// Global count of kernel launches issued through the launchers below (a graph
+// replay adds its node count).  Reported as bench.py's "gpu_launches".
+extern unsigned long long g_launch_count;
+
+// ---------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched at run time; no libcuda link).
+// ---------------------------------------------------------------------------
+// 2D row-major bf16 matrix [rows, cols] with leading dimension ld (elements);
+// box = [box_rows, 64 cols] (128-byte inner extent), SWIZZLE_128B.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows);
+
+// ---------------------------------------------------------------------------
+// GEMM: D[M,N] = A[M,K] * B[N,K]^T, bf16 operands (both K-major), fp32 accumulate
+// in TMEM (tcgen05.mma), TMA-fed smem ring, warp-specialised.
+// ---------------------------------------------------------------------------
+enum GemmEpilogue : int {
+  EPI_BF16 = 0,        // out bf16 [M, ldo] = acc
+  EPI_F32 = 1,         // out f32  [M, ldo] = acc
+  EPI_RESID_F32 = 2,   // out f32  [M, ldo] = acc + resid[M, ldo]      (in place allowed)
+  EPI_GATED_GELU = 3,  // out bf16 [M, N/2]: per 64 acc columns, gelu(acc[0:32]) * acc[32:64]
+  EPI_POS_F32 = 4,     // out f32 = acc + pos[(r % pos_rows - shift[r / pos_rows]) mod pos_rows]
+                       //   optionally duplicated to out[r + dup_rows]
+};
+
+struct GemmArgs {
+  const bf16* A;  // [M, lda]
+  const bf16* B;  // [N, ldb]   (weights packed [out, in])
+  int M, N, K;
+  int lda, ldb;
+  int epilogue;
+  void* out;
+  int ldo;
+  const float* resid;    // EPI_RESID_F32
+  const float* pos;      // EPI_POS_F32: [pos_rows, N]
+  int pos_rows;
+  const int* pos_shift;  // EPI_POS_F32: per (r / pos_rows) roll amount or nullptr
+  int dup_rows;          // EPI_POS_F32: also store to row r + dup_rows when > 0
+  // Pre-built tensor maps (engine caches them); when null the launcher builds them.
+  const CUtensorMap* tmap_a;
+  const CUtensorMap* tmap_b;
+  int block_n;           // 0 = auto (64/128/256)
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+int gemm_configure();  // opt in to the kernels' dynamic shared memory sizes (idempotent)
+// Box rows the A / B maps must be built with for a given block_n choice.
+int gemm_pick_block_n(int M, int N);
+
+// ---------------------------------------------------------------------------
+// Attention: O = softmax(Q K^T + keymask) V, no 1/sqrt(d), head_dim 64.
+// Q rows [nbatch*Lq, ldq], K/V rows [nbatch*Lk, ldk/ldv]; head h uses columns
+// [h*64, h*64+64).  mask_bits: [nbatch, mask_stride_words] uint32 bit per key
+// (1 = attend) or nullptr.  Rows with no attendable key produce 0.
+// ---------------------------------------------------------------------------
+struct AttnArgs {
+  const bf16* Q; int ldq;
+  const bf16* K; int ldk;
+  const bf16* V; int ldv;
+  bf16* O; int ldo;
+  int nbatch, heads, Lq, Lk;
+  const uint32_t* mask_bits; int mask_stride_words;
+  const CUtensorMap* tmap_q; const CUtensorMap* tmap_k; const CUtensorMap* tmap_v;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+int attention_configure();
+
+// ---------------------------------------------------------------------------
+// Row-wise and element-wise kernels
+// ---------------------------------------------------------------------------
+// y = rmsnorm(x; g) [ * (1 + s) + b ], written as bf16.  s|b = film[(*step) * film_stride +
+// film_offset + {0, d}] when film != nullptr.  split3: write [hi | lo | hi] (3*d wide).
+int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* out, int ldo,
+                   const float* film, const int* step, long long film_step_stride,
+                   long long film_offset, int split3, cudaStream_t stream);
+
+struct SamplerArgs {
+  const float* eps;       // [(passes*B)*N, n_dims] rows: cond block then uncond block
+  float* z;               // [B*N*n_dims] state, updated in place
+  bf16* z_split;          // [B*N, 3*n_dims] = [hi | lo | hi] of the new z
+  const float* noise;     // [num_steps, B*N*n_dims] or nullptr -> philox(seed)
+  const float* coef;      // [num_steps, 8]: x0_scale, eps_scale, c_z, c_x0, sigma, last, -, -
+  const int* step;        // device step index i
+  float* mel_out;         // written when i == 0: scale_to_features(z)
+  long long n;            // B*N*n_dims
+  int n_dims;
+  int passes;             // 2 with classifier-free guidance, 1 without
+  float cond_weight;
+  int clip_x0;
+  float feat_min, feat_max;
+  unsigned long long seed;
+};
+int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream);
+int launch_step_advance(int* step, cudaStream_t stream);
+
+// z0 = init (copy or philox normal), plus its [hi | lo | hi] split.
+int launch_init_z(const float* init_z, float* z, bf16* z_split, long long n, int n_dims,
+                  unsigned long long seed, cudaStream_t stream);
+
+// x[b,t,:] = E[tok[b,t]] + P[t]
+int launch_embed_tokens(const int* tokens, const float* emb, const float* pos, float* x, int B,
+                        int T, int d, int vocab, cudaStream_t stream);
+// ctx features -> clip, scale to [-1,1], [hi | lo | hi] split for the input projection
+int launch_scale_split(const float* feat, bf16* out_split, long long rows, int n_dims, float fmin,
+                       float fmax, cudaStream_t stream);
+// key-mask bit words + terminal-relative roll amounts
+int launch_build_masks(const int* tokens, const int* ctx_mask, int B, int T, int C,
+                       uint32_t* bits /*[B,(T+C)/32]*/, int* ctx_seq_len /*[B]*/,
+                       int terminal_relative, cudaStream_t stream);
+// fp32 rows -> bf16 rows (encodings), with row remap b*src_len+t -> b*dst_len+dst_off+t
+int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src_len, int d,
+                              bf16* out, int dst_len, int dst_off, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Load-time kernels
+// ---------------------------------------------------------------------------
+// dst[n_off + n, k_off + k] = cvt(W[k, n]) for W fp32 [K, N] row-major; dst bf16 [*, ldd].
+// part: 0 = bf16(w), 1 = bf16(w - bf16(w)) (low half of the split).
+int launch_pack_weight(const float* W, int K, int N, bf16* dst, int ldd, int n_off, int k_off,
+                       int part, cudaStream_t stream);
+// Gated-MLP pack: dst rows interleave 32 columns of W0 then 32 of W1.
+int launch_pack_gated(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd,
+                      cudaStream_t stream);
+// C[M,N] = act(A[M,K] * B[K,N]) fp32 SIMT (act: 0 none, 1 swish)
+int launch_sgemm_f32(const float* A, const float* B, float* C, int ldc, int M, int N, int K,
+                     int act, cudaStream_t stream);
+// fp32 <-> bf16 row copies and int mask -> bit words (operator-level hooks)
+int launch_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t stream);
+int launch_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t stream);
+int launch_mask_bits(const int* mask, int nb, int L, uint32_t* bits, cudaStream_t stream);
+
+}  // namespace msd

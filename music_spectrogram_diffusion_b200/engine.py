@@ -1,0 +1,189 @@
+"""Thin host wrapper over the C ABI: torch tensors are storage only.
+
+`Engine` owns one `msd_ctx` (one GPU).  It mirrors the operator surface the
+reference exposes one level below `InferenceModel.predict`:
+  encode      <-> module.apply(..., method=module.encode)   models.py:365-371
+  decode_eps  <-> module.apply(..., method=module.decode)   models.py:378-386
+  sample      <-> diffusion_utils.eval_scan + scale_to_features  models.py:393-395
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from music_spectrogram_diffusion_b200 import _native
+from music_spectrogram_diffusion_b200.config import DiffusionConfig, T5Config
+
+
+def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int,
+                    targets_length: int, context_length: int, max_batch: int,
+                    n_dims: int = 128, feature_min: float = math.log(1e-5),
+                    feature_max: float = 4.0) -> _native.MsdConfig:
+  """Translate the reference's config objects into `struct msd_config`."""
+  if tuple(t5.mlp_activations) != ('gelu', 'linear'):
+    raise NotImplementedError(
+        f'mlp_activations={t5.mlp_activations}: only the gated-GELU MLP of the '
+        'diffusion configs (gin/models/diffusion/context/t5_base.gin:79) is built')
+  if t5.decoder_cross_attend_style != 'concat_encodings':
+    raise NotImplementedError('only decoder_cross_attend_style="concat_encodings" is built')
+  if diffusion.model_output != 'eps':
+    raise NotImplementedError('only model_output="eps" is built')
+  sched = diffusion.sampler.schedule
+  if sched.name != 'cosine' or diffusion.train_schedule.name != 'cosine':
+    raise NotImplementedError('only the cosine schedule is built')
+  sampler = {'ddpm': 0, 'ddim': 1}[diffusion.sampler.name]
+  logvar = {'large': 0, 'small': 1}[diffusion.sampler.logvar_type]
+  ctxpos = {'regular': 0, 'terminal_relative': 1}[t5.context_positions]
+  return _native.MsdConfig(
+      vocab_size=t5.vocab_size, emb_dim=t5.emb_dim, num_heads=t5.num_heads,
+      head_dim=t5.head_dim, num_encoder_layers=t5.num_encoder_layers,
+      num_decoder_layers=t5.num_decoder_layers, mlp_dim=t5.mlp_dim,
+      inputs_length=inputs_length, targets_length=targets_length,
+      context_length=context_length, n_dims=n_dims, num_steps=int(sched.num_steps),
+      max_batch=max_batch, sampler=sampler, logvar_type=logvar,
+      clip_x0=int(bool(diffusion.sampler.clip_x0)), context_positions=ctxpos,
+      max_decoder_noise_time=float(t5.max_decoder_noise_time),
+      eval_condition_weight=float(diffusion.classifier_free_guidance.eval_condition_weight),
+      feature_min=float(feature_min), feature_max=float(feature_max))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+  return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device: torch.device) -> ctypes.c_void_p:
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+  """One msd_ctx on one GPU."""
+
+  def __init__(self, cfg: _native.MsdConfig, device: int = 0):
+    self.lib = _native.load()
+    if not torch.cuda.is_available():
+      raise _native.MsdError('no CUDA device: the sm_100a library cannot run (no CPU fallback)')
+    self.cfg = cfg
+    self.device = torch.device('cuda', device)
+    torch.cuda.set_device(self.device)
+    torch.zeros(1, device=self.device)  # make sure the primary context exists
+    handle = ctypes.c_void_p()
+    _native.check(self.lib.msd_create(ctypes.byref(cfg), device, ctypes.byref(handle)),
+                  'msd_create')
+    self._h = handle
+    self._batch = 0
+
+  def close(self) -> None:
+    if getattr(self, '_h', None):
+      self.lib.msd_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  # -- weights ---------------------------------------------------------------
+  def load_weights(self, params: Dict[str, np.ndarray]) -> None:
+    names = sorted(params)
+    arr = (_native.MsdTensor * len(names))()
+    keep = []
+    for i, k in enumerate(names):
+      a = np.ascontiguousarray(params[k], dtype=np.float32)
+      keep.append(a)
+      arr[i].name = k.encode()
+      arr[i].data = a.ctypes.data
+      arr[i].ndim = a.ndim
+      for j, s in enumerate(a.shape):
+        arr[i].shape[j] = s
+    _native.check(self.lib.msd_load_weights(self._h, arr, len(names)), 'msd_load_weights')
+
+  # -- operator surface --------------------------------------------------------
+  def encode(self, tokens: torch.Tensor, ctx_features: torch.Tensor,
+             ctx_mask: torch.Tensor) -> None:
+    b = tokens.shape[0]
+    assert tokens.dtype == torch.int32 and tokens.is_cuda and tokens.is_contiguous()
+    assert ctx_features.dtype == torch.float32 and ctx_features.is_contiguous()
+    assert ctx_mask.dtype == torch.int32 and ctx_mask.is_contiguous()
+    assert tokens.shape == (b, self.cfg.inputs_length), tokens.shape
+    assert ctx_features.shape == (b, self.cfg.context_length, self.cfg.n_dims)
+    assert ctx_mask.shape == (b, self.cfg.context_length)
+    _native.check(self.lib.msd_encode(self._h, _ptr(tokens), _ptr(ctx_features), _ptr(ctx_mask),
+                                      b, _stream(self.device)), 'msd_encode')
+    self._batch = b
+
+  def encodings(self) -> torch.Tensor:
+    out = torch.empty(self._batch, self.cfg.inputs_length + self.cfg.context_length,
+                      self.cfg.emb_dim, dtype=torch.float32, device=self.device)
+    _native.check(self.lib.msd_get_encodings(self._h, _ptr(out), _stream(self.device)),
+                  'msd_get_encodings')
+    return out
+
+  def decode_eps(self, z: torch.Tensor, step_i: int, conditioned: bool) -> torch.Tensor:
+    assert z.dtype == torch.float32 and z.is_cuda and z.is_contiguous()
+    assert z.shape == (self._batch, self.cfg.targets_length, self.cfg.n_dims)
+    out = torch.empty_like(z)
+    _native.check(self.lib.msd_decode_eps(self._h, _ptr(z), step_i, int(conditioned), _ptr(out),
+                                          _stream(self.device)), 'msd_decode_eps')
+    return out
+
+  def sample(self, init_z: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+             seed: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    shape = (self._batch, self.cfg.targets_length, self.cfg.n_dims)
+    if init_z is not None:
+      assert init_z.dtype == torch.float32 and init_z.is_contiguous() and init_z.shape == shape
+    if noise is not None:
+      assert noise.dtype == torch.float32 and noise.is_contiguous()
+      assert noise.shape == (self.cfg.num_steps,) + shape, noise.shape
+    if out is None:
+      out = torch.empty(shape, dtype=torch.float32, device=self.device)
+    _native.check(self.lib.msd_sample(self._h, _ptr(init_z), _ptr(noise), seed, _ptr(out),
+                                      _stream(self.device)), 'msd_sample')
+    return out
+
+  def step_table(self) -> np.ndarray:
+    tab = np.zeros((self.cfg.num_steps, 8), dtype=np.float32)
+    _native.check(self.lib.msd_get_step_table(self._h, tab.ctypes.data), 'msd_get_step_table')
+    return tab
+
+
+def launch_count() -> int:
+  return int(_native.load().msd_launch_count())
+
+
+# ---- operator-level hooks (unit parity with msd/layers.py) --------------------
+def op_dense(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+  lib = _native.load()
+  m, k = a.shape
+  n = w.shape[1]
+  out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+  _native.check(lib.msd_op_dense(_ptr(a.contiguous()), _ptr(w.contiguous()), m, n, k, _ptr(out),
+                                 _stream(a.device)), 'msd_op_dense')
+  return out
+
+
+def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                 key_mask: Optional[torch.Tensor], heads: int) -> torch.Tensor:
+  lib = _native.load()
+  nb, lq, _ = q.shape
+  lk = k.shape[1]
+  out = torch.empty_like(q)
+  _native.check(lib.msd_op_attention(_ptr(q.contiguous()), _ptr(k.contiguous()),
+                                     _ptr(v.contiguous()), _ptr(key_mask), nb, heads, lq, lk,
+                                     _ptr(out), _stream(q.device)), 'msd_op_attention')
+  return out
+
+
+def op_rmsnorm_film(x: torch.Tensor, gamma: torch.Tensor,
+                    film: Optional[torch.Tensor]) -> torch.Tensor:
+  lib = _native.load()
+  rows, d = x.shape
+  out = torch.empty_like(x)
+  _native.check(lib.msd_op_rmsnorm_film(_ptr(x.contiguous()), _ptr(gamma), _ptr(film), rows, d,
+                                        _ptr(out), _stream(x.device)), 'msd_op_rmsnorm_film')
+  return out

@@ -1,0 +1,60 @@
+"""Shared builders for the parity tests (tiny network + seeded inputs)."""
+import numpy as np
+import torch
+
+from music_spectrogram_diffusion_b200 import config, engine, weights
+from oracle import msd_oracle as O
+
+
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+  return t.to(torch.bfloat16).to(torch.float32)
+
+
+def oracle_config(t5, steps, cond_weight, **kw):
+  return O.OracleConfig(
+      vocab_size=t5.vocab_size, emb_dim=t5.emb_dim, num_heads=t5.num_heads,
+      num_encoder_layers=t5.num_encoder_layers, num_decoder_layers=t5.num_decoder_layers,
+      head_dim=t5.head_dim, mlp_dim=t5.mlp_dim, num_steps=steps,
+      eval_condition_weight=cond_weight, **kw)
+
+
+def make_batch(B, T, C, seed=1, pad_second=True, ctx_masks=None):
+  rng = np.random.default_rng(seed)
+  toks = rng.integers(3, 1391, (B, T)).astype(np.int32)
+  toks[:, -1] = 1
+  if pad_second and B > 1:
+    toks[1, T // 2 - 4:] = 0
+  ctx = rng.uniform(np.log(1e-5) - 1.0, 4.5, (B, C, 128)).astype(np.float32)
+  if ctx_masks is None:
+    ctx_masks = [1 if i % 2 == 0 else 0 for i in range(B)]
+  cmask = np.stack([np.full(C, m, np.int32) for m in ctx_masks])
+  return toks, ctx, cmask
+
+
+def make_noise(steps, B, N, seed=0):
+  g = torch.Generator().manual_seed(seed)
+  init_z = torch.randn(B, N, 128, generator=g)
+  noise = torch.randn(steps, B, N, 128, generator=g)
+  return init_z, noise
+
+
+def build_engine(t5, T, N, C, B, steps, cond_weight, params, sampler='ddpm', logvar='large',
+                 clip_x0=True):
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = steps
+  diff.sampler.name = sampler
+  diff.sampler.logvar_type = logvar
+  diff.sampler.clip_x0 = clip_x0
+  diff.classifier_free_guidance.eval_condition_weight = cond_weight
+  eng = engine.Engine(engine.make_msd_config(t5, diff, T, N, C, max_batch=B), 0)
+  eng.load_weights(params)
+  return eng
+
+
+def torch_batch(toks, ctx, cmask, device=None):
+  d = dict(encoder_input_tokens=torch.from_numpy(toks),
+           encoder_continuous_inputs=torch.from_numpy(ctx),
+           encoder_continuous_mask=torch.from_numpy(cmask))
+  if device is not None:
+    d = {k: v.to(device) for k, v in d.items()}
+  return d

@@ -1,0 +1,130 @@
+"""-m gpu: network / sampler parity of the CUDA path (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from music_spectrogram_diffusion_b200 import config, weights
+from oracle import msd_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+T = N = C = 128
+
+
+@pytest.fixture(scope='module')
+def tiny():
+  t5 = config.t5_tiny()
+  params = weights.synthetic_params(t5, T, N, C, seed=0)
+  return t5, params
+
+
+def _rel(a, b):
+  return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def test_step_table(cuda_device, tiny):
+  t5, params = tiny
+  eng = H.build_engine(t5, T, N, C, 1, 1000, 2.0, params)
+  tab = eng.step_table()
+  for i in (999, 998, 500, 1):
+    ref = O.sampler_coefficients(i, 1000, dtype=np.float32)
+    got = tab[i]
+    np.testing.assert_allclose(got[0], ref['x0_scale'], rtol=2e-3)   # fp32 tan near pi/2
+    np.testing.assert_allclose(got[1], ref['eps_scale'], rtol=1e-4)
+    np.testing.assert_allclose(got[2], ref['c_z'], rtol=2e-3)
+    np.testing.assert_allclose(got[3], ref['c_x0'], rtol=2e-3)
+    np.testing.assert_allclose(got[4], ref['sigma'], rtol=1e-4)
+  assert tab[0][5] == 1.0 and tab[1][5] == 0.0
+  eng.close()
+
+
+def test_encode(cuda_device, tiny):
+  t5, params = tiny
+  B = 3
+  toks, ctx, cmask = H.make_batch(B, T, C, ctx_masks=[1, 0, 1])
+  cmask[2, 40:] = 0   # partially filled context -> terminal-relative roll by 40
+  eng = H.build_engine(t5, T, N, C, B, 4, 2.0, params)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+             b['encoder_continuous_mask'])
+  got = eng.encodings().cpu()
+  oc = H.oracle_config(t5, 4, 2.0)
+  cb = H.torch_batch(toks, ctx, cmask)
+  encs = O.encode(O.params_to(params), oc, cb['encoder_input_tokens'],
+                  O.scale_features(cb['encoder_continuous_inputs'], oc, clip=True),
+                  cb['encoder_continuous_mask'])
+  want = torch.cat([encs[0][0], encs[1][0]], dim=1)
+  valid = torch.cat([encs[0][1], encs[1][1]], dim=1) > 0   # only unmasked positions are defined
+  err = ((got - want).abs() * valid.unsqueeze(-1)).max().item()
+  assert torch.isfinite(got).all()
+  assert err < 6e-2, f'max err on valid positions {err}'
+  eng.close()
+
+
+@pytest.mark.parametrize('conditioned', [True, False])
+def test_decode_eps(cuda_device, tiny, conditioned):
+  t5, params = tiny
+  B, steps = 2, 16
+  toks, ctx, cmask = H.make_batch(B, T, C)
+  eng = H.build_engine(t5, T, N, C, B, steps, 2.0, params)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+             b['encoder_continuous_mask'])
+  z = torch.randn(B, N, 128, generator=torch.Generator().manual_seed(3))
+  oc = H.oracle_config(t5, steps, 2.0)
+  P = O.params_to(params)
+  cb = H.torch_batch(toks, ctx, cmask)
+  encs = O.encode(P, oc, cb['encoder_input_tokens'],
+                  O.scale_features(cb['encoder_continuous_inputs'], oc, clip=True),
+                  cb['encoder_continuous_mask'])
+  flag = 1.0 if conditioned else 0.0
+  for step_i in (steps - 1, 5, 0):
+    got = eng.decode_eps(z.to(cuda_device), step_i, conditioned).cpu()
+    t = np.float32(step_i + 1.0) / np.float32(steps)
+    want = O.decode(P, oc, [(e * flag, m * flag) for e, m in encs], z,
+                    torch.full((B,), float(t)))
+    rel = ((got - want).abs().max() / want.abs().max()).item()
+    assert rel < 3e-2, f'step {step_i}: rel max err {rel}'
+  eng.close()
+
+
+@pytest.mark.parametrize('sampler,weight', [('ddpm', 2.0), ('ddim', 2.0), ('ddpm', 1.0)])
+def test_sample_matches_oracle(cuda_device, tiny, sampler, weight):
+  t5, params = tiny
+  B, steps = 2, 12
+  toks, ctx, cmask = H.make_batch(B, T, C)
+  init_z, noise = H.make_noise(steps, B, N)
+  eng = H.build_engine(t5, T, N, C, B, steps, weight, params, sampler=sampler)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+             b['encoder_continuous_mask'])
+  mel = eng.sample(init_z.to(cuda_device), noise.to(cuda_device)).cpu()
+  oc = H.oracle_config(t5, steps, weight, sampler=sampler)
+  ref, scores = O.predict_batch_with_aux(O.params_to(params), oc, H.torch_batch(toks, ctx, cmask),
+                                         init_z, noise)
+  span = oc.max_value - oc.min_value
+  err = (mel - ref).abs() / span * 2.0     # normalised [-1, 1] units
+  assert torch.isfinite(mel).all()
+  # tolerance (bf16 operand path): mean |d| <= 3e-2 in normalised units
+  assert err.mean().item() < 3e-2, f'mean {err.mean().item()} max {err.max().item()}'
+  eng.close()
+
+
+def test_sample_internal_rng_is_deterministic(cuda_device, tiny):
+  t5, params = tiny
+  B, steps = 1, 6
+  toks, ctx, cmask = H.make_batch(B, T, C)
+  eng = H.build_engine(t5, T, N, C, B, steps, 2.0, params)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+             b['encoder_continuous_mask'])
+  a = eng.sample(seed=7).clone()
+  b2 = eng.sample(seed=7).clone()
+  c = eng.sample(seed=8).clone()
+  assert torch.equal(a, b2)
+  assert not torch.equal(a, c)
+  assert torch.isfinite(a).all()
+  lo, hi = np.log(1e-5) - 1e-3, 4.0 + 1e-3
+  assert a.min().item() >= lo and a.max().item() <= hi
+  eng.close()

@@ -1,0 +1,72 @@
+"""-m gpu: operator-level parity of the sm_100a kernels against the oracle's restatement of
+msd/layers.py (same shape of test as layers_test.py:375-387 / 285-330 / 450-484, at sizes the
+tensor-core kernels accept)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import msd_oracle as O
+from tests.helpers import bf16_round
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 384, 128), (512, 2304, 768),
+                                   (128, 64, 384), (384, 256, 2048)])
+def test_dense_general(cuda_device, M, N, K):
+  from music_spectrogram_diffusion_b200 import engine
+  g = torch.Generator().manual_seed(M + N + K)
+  a = bf16_round(torch.randn(M, K, generator=g))
+  w = bf16_round(torch.randn(K, N, generator=g) / np.sqrt(K))
+  got = engine.op_dense(a.to(cuda_device), w.to(cuda_device)).cpu()
+  want = O.dense_general(a.double(), w.double()).float()
+  err = (got - want).abs().max().item()
+  assert err < 2e-4 * np.sqrt(K), f'max err {err}'
+
+
+@pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
+    (1, 1, 128, 128, False), (2, 2, 128, 256, False), (2, 3, 256, 384, True),
+    (1, 2, 256, 2304, True), (3, 2, 128, 128, True)])
+def test_dot_product_attention(cuda_device, nb, heads, Lq, Lk, masked):
+  from music_spectrogram_diffusion_b200 import engine
+  g = torch.Generator().manual_seed(nb * 1000 + Lk)
+  w = heads * 64
+  q = bf16_round(torch.randn(nb, Lq, w, generator=g) * 0.5)
+  k = bf16_round(torch.randn(nb, Lk, w, generator=g) * 0.5)
+  v = bf16_round(torch.randn(nb, Lk, w, generator=g))
+  mask = None
+  bias = None
+  if masked:
+    mask = (torch.rand(nb, Lk, generator=g) > 0.3).to(torch.int32)
+    mask[0, Lk // 2:] = 0                      # a run of fully masked key blocks
+    if nb > 2:
+      mask[2, :] = 0                           # a row with nothing to attend to -> zeros
+    qm = torch.ones(nb, Lq)
+    m4 = O.make_attention_mask(qm, mask.float())
+    bias = torch.where(m4 > 0, torch.zeros_like(m4), torch.full_like(m4, -1e10))
+  want = O.dot_product_attention(q.view(nb, Lq, heads, 64), k.view(nb, Lk, heads, 64),
+                                 v.view(nb, Lk, heads, 64), bias).reshape(nb, Lq, w)
+  if masked:
+    want = O.zero_activations_if_masked(want, m4)
+  got = engine.op_attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device),
+                            None if mask is None else mask.to(cuda_device), heads).cpu()
+  err = (got - want).abs().max().item()
+  assert torch.isfinite(got).all()
+  assert err < 3e-2, f'max err {err}'
+
+
+@pytest.mark.parametrize('rows,d,film', [(128, 128, False), (256, 768, True), (100, 512, True)])
+def test_layer_norm_film(cuda_device, rows, d, film):
+  from music_spectrogram_diffusion_b200 import engine
+  g = torch.Generator().manual_seed(rows + d)
+  x = torch.randn(rows, d, generator=g) * 3
+  gamma = 1 + 0.1 * torch.randn(d, generator=g)
+  fv = torch.randn(2 * d, generator=g) * 0.2 if film else None
+  want = O.layer_norm(x, gamma)
+  if film:
+    want = want * (fv[:d] + 1.0) + fv[d:]
+  got = engine.op_rmsnorm_film(x.to(cuda_device), gamma.to(cuda_device),
+                               None if fv is None else fv.to(cuda_device)).cpu()
+  err = (got - want).abs().max().item()
+  assert err < 4e-2, f'max err {err}'   # bf16 output rounding of O(4) values
+  assert (got - bf16_round(want)).abs().max().item() < 2e-2
