@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the DDPM sampling hot path (BASELINE.json metric: mel-frames/sec,
+base_with_context, 1000-step DDPM).
+
+  python bench.py --gpus N --steps K --warmup W        # this repo's sm_100a path
+  python bench.py --impl reference ...                 # the CPU oracle port on the host cores
+
+A "step" is one pass of the hot path over one batch: `predict` of `--segments` independent
+5.12 s segments per GPU (encode + num_steps reverse-diffusion steps + unscale).  Under torchrun
+every rank runs the same per-GPU workload (weak scaling, no data-path collective); timing is
+barrier + synchronize on both sides, CUDA events on the device, max over ranks.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_RATE = 50.0  # 16000 / 320, msd/audio_codecs.py:162-164, 209-210
+
+
+def flops_model(t5, lengths, passes=2):
+  """Algorithmic FLOPs (2 per multiply-add), SURVEY App. C: (per diffusion step per segment,
+  once per segment), with cross K/V hoisted, the unconditional cross-attention elided and the
+  FiLM/time tables precomputed."""
+  d, hh, F = t5.emb_dim, t5.num_heads * t5.head_dim, t5.mlp_dim
+  N, T, C = lengths['targets'], lengths['inputs'], lengths['targets_context']
+  M = T + C
+  self_attn = 2 * N * d * 3 * hh + 2 * N * hh * d + 2 * 2 * N * N * hh
+  cross = 2 * N * d * hh + 2 * N * hh * d + 2 * 2 * N * M * hh
+  mlp = 3 * 2 * N * d * F
+  inout = 2 * 2 * N * 128 * d
+  L = t5.num_decoder_layers
+  cond = (self_attn + cross + mlp) * L + inout
+  uncond = (self_attn + mlp) * L + inout
+  per_step = cond + (uncond if passes == 2 else 0)
+
+  def enc(S):
+    return t5.num_encoder_layers * (2 * S * d * 3 * hh + 2 * S * hh * d + 2 * 2 * S * S * hh +
+                                    3 * 2 * S * d * F)
+  once = L * 2 * M * d * 2 * hh + enc(T) + enc(C)
+  return per_step, once
+
+
+def as_written_flops(t5, lengths):
+  """FLOPs of the graph exactly as the reference writes it (what the CPU oracle executes)."""
+  d, hh, F = t5.emb_dim, t5.num_heads * t5.head_dim, t5.mlp_dim
+  N, T, C = lengths['targets'], lengths['inputs'], lengths['targets_context']
+  M = T + C
+  L = t5.num_decoder_layers
+  self_attn = 2 * N * d * 3 * hh + 2 * N * hh * d + 2 * 2 * N * N * hh
+  cross = 2 * N * d * hh + 2 * N * hh * d + 2 * 2 * N * M * hh + 2 * M * d * 2 * hh
+  mlp = 3 * 2 * N * d * F
+  film = 2 * 2 * 4 * d * 2 * d
+  one_pass = (self_attn + cross + mlp + film) * L + 2 * 2 * N * 128 * d + 2 * d * 4 * d + 2 * 16 * d * d
+  return 2 * one_pass
+
+
+class ClockSampler(threading.Thread):
+  """Samples SM clock / throttle reasons of the local GPU during the timed region."""
+  BAD = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20}
+  NOTE = {'sw_power_cap': 0x4}
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index = index
+    self.samples = []
+    self.reasons = set()
+    self.max_mhz = None
+    self._stop = threading.Event()
+    self.ok = False
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+      self.ok = True
+    except Exception:  # pylint: disable=broad-except
+      self.ok = False
+
+  def run(self):
+    if not self.ok:
+      return
+    while not self._stop.is_set():
+      try:
+        self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        for k, bit in {**self.BAD, **self.NOTE}.items():
+          if mask & bit:
+            self.reasons.add(k)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      self._stop.wait(0.2)
+
+  def finish(self):
+    self._stop.set()
+    if self.is_alive():
+      self.join(timeout=2)
+    med = int(np.median(self.samples)) if self.samples else None
+    return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+            'samples': len(self.samples)}
+
+
+def synthetic_batch(B, lengths, seed):
+  """unpadded 2048-token segments, full previous-segment context."""
+  rng = np.random.default_rng(seed)
+  toks = rng.integers(3, 1391, (B, lengths['inputs'])).astype(np.int32)
+  toks[:, -1] = 1
+  ctx = rng.uniform(math.log(1e-5), 4.0, (B, lengths['targets_context'], 128)).astype(np.float32)
+  cmask = np.ones((B, lengths['targets_context']), np.int32)
+  tgt = np.zeros((B, lengths['targets'], 128), np.float32)
+  return dict(encoder_input_tokens=toks, encoder_continuous_inputs=ctx,
+              encoder_continuous_mask=cmask, decoder_target_tokens=tgt)
+
+
+def model_configs(args):
+  from music_spectrogram_diffusion_b200 import config
+  t5 = {'base': config.t5_base, 'small': config.t5_small, 'tiny': config.t5_tiny}[args.model]()
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = args.diffusion_steps
+  # The colab "serve" path runs guidance weight 2.0 (ipynb:223); any weight != 1 costs the same.
+  diff.classifier_free_guidance.eval_condition_weight = 2.0
+  lengths = dict(config.TASK_FEATURE_LENGTHS_CONTEXT)
+  if args.model == 'tiny':
+    lengths = {'inputs': 128, 'targets': 128, 'targets_context': 128}
+  return t5, diff, lengths
+
+
+_ORACLE_PARAMS = {}
+
+
+def cpu_oracle_sample(t5, diff, lengths, n_steps, threads):
+  """Time the oracle port (graph AS WRITTEN) on one segment: encode + n_steps full CFG steps;
+  returns (seconds_encode, seconds_per_step)."""
+  import torch
+  from music_spectrogram_diffusion_b200 import weights
+  from oracle import msd_oracle as O
+  torch.set_num_threads(threads)
+  key = (t5.emb_dim, t5.num_decoder_layers, lengths['inputs'])
+  if key not in _ORACLE_PARAMS:
+    _ORACLE_PARAMS[key] = O.params_to(weights.synthetic_params(
+        t5, lengths['inputs'], lengths['targets'], lengths['targets_context'], seed=0))
+  params = _ORACLE_PARAMS[key]
+  oc = O.OracleConfig(vocab_size=t5.vocab_size, emb_dim=t5.emb_dim, num_heads=t5.num_heads,
+                      num_encoder_layers=t5.num_encoder_layers,
+                      num_decoder_layers=t5.num_decoder_layers, head_dim=t5.head_dim,
+                      mlp_dim=t5.mlp_dim, num_steps=diff.sampler.schedule.num_steps,
+                      eval_condition_weight=2.0)
+  b = synthetic_batch(1, lengths, seed=0)
+  g = torch.Generator().manual_seed(0)
+  z = torch.randn(1, lengths['targets'], 128, generator=g)
+  with torch.no_grad():
+    t0 = time.perf_counter()
+    ctx = O.scale_features(torch.from_numpy(b['encoder_continuous_inputs']), oc, clip=True)
+    encs = O.encode(params, oc, torch.from_numpy(b['encoder_input_tokens']), ctx,
+                    torch.from_numpy(b['encoder_continuous_mask']))
+    t_enc = time.perf_counter() - t0
+
+    def pred_fn(zz, time_, cond):
+      f = 1.0 if cond else 0.0
+      return O.decode(params, oc, [(e * f, m * f) for e, m in encs], zz, time_)
+
+    t0 = time.perf_counter()
+    i0 = oc.num_steps - 1
+    for k in range(n_steps):
+      z = O.eval_step(z, i0 - k, torch.randn(z.shape, generator=g), pred_fn, oc)
+    t_step = (time.perf_counter() - t0) / n_steps
+  return t_enc, t_step
+
+
+def run_reference(args):
+  """--impl reference: the reference's own algorithm on the host cores.  The JAX reference is
+  not installable here (no jax/flax/t5x wheels), so this is the oracle port, graph as written."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  t5, diff, lengths = model_configs(args)
+  cores = len(os.sched_getaffinity(0))
+  n_cpu_steps = args.cpu_steps
+  times = []
+  for it in range(args.warmup + args.steps):
+    t_enc, t_step = cpu_oracle_sample(t5, diff, lengths, n_cpu_steps, cores)
+    sec = t_enc + diff.sampler.schedule.num_steps * t_step
+    if it >= args.warmup:
+      times.append(sec)
+  sec = float(np.mean(times))
+  value = lengths['targets'] / sec
+  sample = (f'1 segment: encode + {n_cpu_steps} full CFG diffusion steps of the graph as written, '
+            f'extrapolated linearly to {diff.sampler.schedule.num_steps} steps')
+  line = {
+      'impl': 'reference', 'metric': 'mel-frames/sec', 'value': value, 'unit': 'frames/s',
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'x_realtime': value / FRAME_RATE,
+      'config': workload_config(args, t5, lengths, segments=1),
+      'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                       'sample': sample},
+      'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line))
+
+
+def workload_config(args, t5, lengths, segments):
+  return {
+      'workload': f'{args.model}_with_context, {segments} segments/GPU x {lengths["targets"]} '
+                  f'frames, {args.diffusion_steps}-step DDPM, CFG weight 2.0, '
+                  f'{lengths["inputs"]}-token unpadded MIDI segments + full context',
+      'segments_per_gpu': segments, 'diffusion_steps': args.diffusion_steps,
+      'emb_dim': t5.emb_dim, 'layers': t5.num_decoder_layers,
+      'l2_policy': 'working set per diffusion step (weights 227 MB + cross K/V 85 MB/segment) '
+                   'exceeds the 126 MB L2; no explicit flush needed',
+      'parallelism': f'dp{args.gpus} (independent segments, no collective in the loop)',
+  }
+
+
+def peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    with open(p) as f:
+      j = json.load(f)
+    return j.get('bf16_tflops_sustained', 1388.2), j.get('hbm_gbs', 6483.9), 'measured'
+  return 1400.0, 6650.0, 'fallback'
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  from music_spectrogram_diffusion_b200 import engine as eng_mod
+  from music_spectrogram_diffusion_b200 import inference
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  dev = torch.device('cuda', local)
+  torch.cuda.set_device(dev)
+
+  t5, diff, lengths = model_configs(args)
+  B = args.segments
+  model = inference.InferenceModel.from_config(
+      t5, diff, lengths, checkpoint_path='synthetic:0', batch_size=B, device=local)
+  eng = model.engine
+  batch = synthetic_batch(B, lengths, seed=100 + rank)
+  d_tok = torch.from_numpy(batch['encoder_input_tokens']).to(dev)
+  d_ctx = torch.from_numpy(batch['encoder_continuous_inputs']).to(dev)
+  d_msk = torch.from_numpy(batch['encoder_continuous_mask']).to(dev)
+  d_mel = torch.empty(B, lengths['targets'], 128, device=dev)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+
+  def device_step():
+    eng.encode(d_tok, d_ctx, d_msk)
+    eng.sample(None, None, seed=0, out=d_mel)
+
+  def host_step():
+    return model.predict(batch, seed=0)
+
+  def timed(fn, warmup, steps):
+    for _ in range(warmup):
+      fn()
+    barrier()
+    launches0 = eng_mod.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.finish()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / 1e3, wall, clocks, eng_mod.launch_count() - launches0
+
+  sec, wall, clocks, launches = timed(device_step, args.warmup, args.steps)
+  frames = world * B * lengths['targets'] * args.steps
+  value = frames / sec
+  sec_e2e, wall_e2e, clocks_e2e, _ = timed(host_step, max(1, args.warmup // 2), args.steps)
+  value_e2e = frames / sec_e2e
+
+  # ---- roofline of the dominant kernel class (tcgen05 GEMM), CUDA events per launch -------
+  prof = None
+  if rank == 0:
+    eng.encode(d_tok, d_ctx, d_msk)
+    prof = eng.profile_step(step_i=args.diffusion_steps // 2 or 1, reps=3)
+    torch.cuda.synchronize(dev)
+  peak_tf, peak_hbm, peak_kind = peaks()
+  per_step, once = flops_model(t5, lengths)
+  alg_flops_per_frame = (per_step * args.diffusion_steps + once) / lengths['targets']
+
+  if rank == 0:
+    total_ms = sum(v['ms'] for v in prof.values())
+    g = prof['gemm']
+    gemm_tf = g['flops'] / (g['ms'] * 1e-3) / 1e12 if g['ms'] > 0 else 0.0
+    a = prof['attention']
+    attn_tf = a['flops'] / (a['ms'] * 1e-3) / 1e12 if a['ms'] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'gemm_traffic.json')
+    if os.path.exists(tpath):
+      with open(tpath) as f:
+        traffic = json.load(f).get('dram_bytes_per_launch')
+    roofline = {
+        'kernel': 'gemm_bf16_tcgen05_kernel', 'bound': 'tensor',
+        'achieved': gemm_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+        'frac': gemm_tf / peak_tf, 'peak_source': f'{peak_kind} (bf16 sustained)',
+        'traffic': traffic,
+        'launches_per_diffusion_step': g['launches'],
+        'avg_launch_us': 1e3 * g['ms'] / max(g['launches'], 1),
+        'share_of_step': g['ms'] / total_ms if total_ms > 0 else None,
+        'how': 'CUDA events around every launch of one uncaptured diffusion step (3 reps)',
+    }
+    step_tf = alg_flops_per_frame * (value / world) / 1e12
+    line = {
+        'metric': 'mel-frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16', 'data': 'synthetic',
+        'x_realtime': value / FRAME_RATE,
+        'config': workload_config(args, t5, lengths, B),
+        'clocks': clocks,
+        'e2e': {'value': value_e2e, 'unit': 'frames/s',
+                'h2d_bytes_per_step': int(sum(batch[k].nbytes for k in (
+                    'encoder_input_tokens', 'encoder_continuous_inputs',
+                    'encoder_continuous_mask'))),
+                'd2h_bytes_per_step': int(B * lengths['targets'] * 128 * 4),
+                'x_realtime': value_e2e / FRAME_RATE, 'clocks': clocks_e2e,
+                'api': 'InferenceModel.predict(host numpy batch) incl. pinned H2D and D2H'},
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+        'whole_step': {
+            'algorithmic_gflop_per_frame': alg_flops_per_frame / 1e9,
+            'achieved_tflops_per_gpu': step_tf, 'frac_of_peak': step_tf / peak_tf,
+            'wall_seconds': wall,
+        },
+        'kernel_classes_ms_per_diffusion_step': {k: round(v['ms'], 4) for k, v in prof.items()},
+        'attention_tflops': attn_tf,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      cores = len(os.sched_getaffinity(0))
+      t_enc, t_step = cpu_oracle_sample(t5, diff, lengths, args.cpu_steps, cores)
+      cpu_sec = t_enc + args.diffusion_steps * t_step
+      line['cpu_baseline'] = {
+          'value': lengths['targets'] / cpu_sec, 'unit': 'frames/s', 'cores': cores,
+          'kind': 'port',
+          'sample': f'oracle (torch-CPU fp32, graph as written, '
+                    f'{as_written_flops(t5, lengths) / 1e9:.1f} GFLOP/step): 1 segment, encode '
+                    f'({t_enc:.2f} s) + {args.cpu_steps} CFG steps ({t_step:.3f} s each), '
+                    f'extrapolated to {args.diffusion_steps} steps',
+      }
+    print(json.dumps(line))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=3)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--model', default='base', choices=['base', 'small', 'tiny'])
+  ap.add_argument('--segments', type=int, default=8, help='segments per GPU (B)')
+  ap.add_argument('--diffusion-steps', type=int, default=1000)
+  ap.add_argument('--cpu-steps', type=int, default=2,
+                  help='diffusion steps in the bounded CPU sample')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == '__main__':
+  main()

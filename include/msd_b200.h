@@ -109,6 +109,14 @@ int msd_get_encodings(msd_ctx* ctx, float* enc_out, void* stream);
  * x0_scale, eps_scale, c_z, c_x0, sigma, is_last, logsnr_t, logsnr_s. */
 int msd_get_step_table(msd_ctx* ctx, float* table_host);
 
+/* Profiling hook: runs diffusion step `step_i` (1 <= step_i < num_steps) of the batch of the
+ * last msd_encode `reps` times WITHOUT graph capture, bracketing every kernel launch with CUDA
+ * events on the launching stream.  out[5][4] (doubles), one row per kernel class
+ * {0 gemm, 1 attention, 2 rmsnorm/FiLM, 3 sampler, 4 other}:
+ * {milliseconds per step, launches per step, algorithmic FLOPs per step, algorithmic bytes per
+ * step}.  Leaves the sampler state (z) modified; call msd_sample afterwards as usual. */
+int msd_profile_step(msd_ctx* ctx, int32_t step_i, int32_t reps, double* out);
+
 /* Kernel launches issued so far by this library in this process (graph replays count their
  * kernel nodes). */
 uint64_t msd_launch_count(void);

@@ -300,6 +300,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   d.O = a.O; d.ldo = a.ldo; d.heads = a.heads; d.Lq = a.Lq; d.Lk = a.Lk;
   d.mask_bits = a.mask_bits; d.mask_stride_words = a.mask_stride_words;
   dim3 grid(a.Lq / BQ, a.heads, a.nbatch);
+  ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
+                 2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
   attention_tcgen05_kernel<<<grid, 192, ATTN_SMEM, stream>>>(tq, tk, tv, d);
   MSD_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;

@@ -395,6 +395,7 @@ int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* ou
   p.film_step_stride = film_step_stride; p.film_offset = film_offset;
   p.rows = rows; p.d = d; p.ldo = ldo; p.split3 = split3;
   p.src_len = 0; p.dst_len = 0; p.dst_off = 0;
+  ProfScope prof(KC_NORM, 0.0, static_cast<double>(rows) * d * (4.0 + (split3 ? 6.0 : 2.0)), stream);
   rmsnorm_film_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(p);
   MSD_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
@@ -417,6 +418,7 @@ int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src
 
 int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream) {
   MSD_REQUIRE(a.n % 4 == 0 && a.n_dims % 4 == 0, "sampler: sizes must be multiples of 4");
+  ProfScope prof(KC_SAMPLER, 0.0, static_cast<double>(a.n) * (4.0 * (a.passes + 3) + 6.0), stream);
   sampler_step_kernel<<<blocks_for(a.n / 4, 256), 256, 0, stream>>>(a);
   MSD_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
@@ -424,6 +426,7 @@ int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream) {
 }
 
 int launch_step_advance(int* step, cudaStream_t stream) {
+  ProfScope prof(KC_OTHER, 0.0, 8.0, stream);
   step_advance_kernel<<<1, 1, 0, stream>>>(step);
   MSD_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;

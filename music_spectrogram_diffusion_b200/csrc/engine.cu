@@ -40,6 +40,24 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---------------------------------------------------------------------------
+// per-launch profiling recorder
+// ---------------------------------------------------------------------------
+struct ProfRecorder {
+  struct Rec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+};
+ProfRecorder* g_prof = nullptr;
+void prof_begin(int cls, double flops, double bytes, cudaStream_t st) {
+  ProfRecorder::Rec r;
+  r.cls = cls; r.flops = flops; r.bytes = bytes;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof->recs.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof->recs.back().e1, st); }
+
+// ---------------------------------------------------------------------------
 // TMA tensor map encoder (driver entry point resolved through the runtime)
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -844,6 +862,45 @@ int msd_sample(msd_ctx* c, const float* init_z, const float* noise, uint64_t see
     g_launch_count += c->graph_nodes;
   }
   MSD_TRY(end_on(c, caller));
+  return 0;
+}
+
+int msd_profile_step(msd_ctx* c, int32_t step_i, int32_t reps, double* out) {
+  MSD_REQUIRE(c && out && reps >= 1, "msd_profile_step: bad argument");
+  MSD_REQUIRE(c->cur_batch > 0, "msd_profile_step: call msd_encode first");
+  MSD_REQUIRE(step_i >= 1 && step_i < c->cfg.num_steps, "msd_profile_step: step out of range");
+  MSD_CUDA_CHECK(cudaSetDevice(c->device));
+  cudaStream_t st = c->work;
+  const int B = c->cur_batch;
+  ProfRecorder rec;
+  for (int i = 0; i < 4 * KC_COUNT; ++i) out[i] = 0.0;
+  const unsigned long long before = g_launch_count;
+  int rc = 0;
+  for (int r = 0; r < reps + 1 && rc == 0; ++r) {
+    // repetition 0 is an untimed warm-up; z just keeps evolving, the work per step is identical
+    MSD_CUDA_CHECK(cudaMemcpyAsync(c->d_step, &step_i, sizeof(int), cudaMemcpyHostToDevice, st));
+    MSD_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (r == 1) g_prof = &rec;
+    rc = run_decoder(c, B, B, c->passes * B, st);
+    if (rc == 0) rc = sampler_step(c, B, nullptr, 1234, nullptr, st);
+    if (rc == 0) rc = launch_step_advance(c->d_step, st);
+  }
+  g_prof = nullptr;
+  g_launch_count = before;
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (auto& r : rec.recs) {
+    float ms = 0.f;
+    if (e == cudaSuccess && rc == 0 && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      out[r.cls * 4 + 0] += ms / reps;
+      out[r.cls * 4 + 1] += 1.0 / reps;
+      out[r.cls * 4 + 2] += r.flops / reps;
+      out[r.cls * 4 + 3] += r.bytes / reps;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  if (rc != 0) return rc;
+  MSD_CUDA_CHECK(e);
   return 0;
 }
 

@@ -213,6 +213,9 @@ template <int BN>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   dim3 grid(d.N / BN, (d.M + BLOCK_M - 1) / BLOCK_M);
+  ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
+                 2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
+                     4.0 * d.M * d.N, st);
   gemm_bf16_tcgen05_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, d);
   MSD_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;

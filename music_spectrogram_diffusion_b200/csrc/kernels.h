@@ -15,6 +15,27 @@ typedef __nv_bfloat16 bf16;
 extern unsigned long long g_launch_count;
 
 // ---------------------------------------------------------------------------
+// Optional per-launch profiling (msd_profile_step): when a recorder is armed every launcher
+// brackets its kernel with CUDA events on the launching stream and notes its algorithmic work.
+// ---------------------------------------------------------------------------
+enum KernelClass : int { KC_GEMM = 0, KC_ATTENTION = 1, KC_NORM = 2, KC_SAMPLER = 3, KC_OTHER = 4,
+                         KC_COUNT = 5 };
+struct ProfRecorder;
+extern ProfRecorder* g_prof;
+void prof_begin(int cls, double flops, double bytes, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t s) : st(s), on(g_prof != nullptr) {
+    if (on) prof_begin(cls, flops, bytes, st);
+  }
+  ~ProfScope() {
+    if (on) prof_end(st);
+  }
+};
+
+// ---------------------------------------------------------------------------
 // TMA tensor maps (driver entry point fetched at run time; no libcuda link).
 // ---------------------------------------------------------------------------
 // 2D row-major bf16 matrix [rows, cols] with leading dimension ld (elements);

@@ -146,6 +146,17 @@ class Engine:
                                       _stream(self.device)), 'msd_sample')
     return out
 
+  KERNEL_CLASSES = ('gemm', 'attention', 'rmsnorm_film', 'sampler', 'other')
+
+  def profile_step(self, step_i: int = 500, reps: int = 3) -> Dict[str, Dict[str, float]]:
+    """Per-kernel-class CUDA-event timing of one diffusion step (uncaptured)."""
+    out = np.zeros((5, 4), dtype=np.float64)
+    _native.check(self.lib.msd_profile_step(self._h, step_i, reps, out.ctypes.data),
+                  'msd_profile_step')
+    return {name: dict(ms=float(out[i, 0]), launches=float(out[i, 1]), flops=float(out[i, 2]),
+                       bytes=float(out[i, 3]))
+            for i, name in enumerate(self.KERNEL_CLASSES)}
+
   def step_table(self) -> np.ndarray:
     tab = np.zeros((self.cfg.num_steps, 8), dtype=np.float32)
     _native.check(self.lib.msd_get_step_table(self._h, tab.ctypes.data), 'msd_get_step_table')
