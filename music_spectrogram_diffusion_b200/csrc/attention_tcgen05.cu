@@ -3,15 +3,18 @@
 // msd/layers.py:341-348 (0 / -1e10 bias == masked keys get exactly zero weight in fp32), and
 // rows with no attendable key produce 0 (msd/layers.py:882-902 zero_activations_if_masked).
 //
-// One CTA per (128-query block, head, batch row):
-//   warp 0 (one lane)  TMA producer: Q tile once, then K/V 128-key tiles into a 2-deep ring
-//   warp 1 (one lane)  MMA issuer:   S = Q K^T   (M128 x N128 x K64, both operands K-major)
-//                                    PV = P V    (M128 x N64 x K128, P K-major from smem,
-//                                                 V MN-major straight from its [key, 64] tile)
-//   warps 2..5         softmax: thread = query row; S read from TMEM (tcgen05.ld), online
-//                      max / exp2 / sum in fp32, P written to smem as bf16 in the 128B-swizzled
-//                      K-major layout, PV partials pulled from TMEM and accumulated in registers
-// Key blocks whose 128 mask bits are all zero are skipped by all three roles.
+// One CTA per (256-query group, head, batch row): TWO 128-query tiles ping-pong so that the
+// tensor core works on one tile while the other tile's softmax runs (the exp throughput of the
+// SFU, not the tensor core, bounds head_dim-64 attention on this part).
+//   warp 0 (one lane)   TMA producer: both Q tiles once, then K/V 128-key tiles into a ring
+//   warp 1 (one lane)   MMA issuer:   S_t = Q_t K^T  (M128 x N128 x K64, both operands K-major)
+//                                     PV_t = P_t V   (M128 x N64 x K128, P K-major from smem,
+//                                                     V MN-major straight from its [key,64] tile)
+//   warps 2..5 / 6..9   softmax group of tile 0 / tile 1: thread = query row; S read from TMEM
+//                       (tcgen05.ld), online max / exp2 / sum in fp32, P written to smem as bf16
+//                       in the 128B-swizzled K-major layout, PV partials pulled from TMEM and
+//                       accumulated (with the running rescale) in registers
+// Key blocks whose 128 mask bits are all zero are skipped by every role.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,15 +22,16 @@ namespace msd {
 
 namespace {
 
-constexpr int BQ = 128;   // queries per CTA
+constexpr int BQ = 128;   // queries per tile
 constexpr int BKV = 128;  // keys per block
 constexpr int HD = 64;    // head dim
-constexpr int Q_BYTES = BQ * HD * 2;        // 16 KB
+constexpr int Q_BYTES = BQ * HD * 2;         // 16 KB per tile
 constexpr int KV_TILE_BYTES = BKV * HD * 2;  // 16 KB
-constexpr int KV_STAGES = 2;
-constexpr int P_BYTES = BQ * BKV * 2;  // 32 KB (two [128 x 64] swizzled sub-tiles)
-constexpr int ATTN_SMEM = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES + 256 + 1024;
-constexpr uint32_t ATTN_TMEM_COLS = 256;  // S: [0,128)  PV: [128,192)
+constexpr int KV_STAGES = 3;
+constexpr int P_BYTES = BQ * BKV * 2;  // 32 KB per tile (two [128 x 64] swizzled sub-tiles)
+constexpr int ATTN_SMEM = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES + 256 + 1024;
+constexpr uint32_t ATTN_TMEM_COLS = 512;  // S0 [0,128) S1 [128,256) PV0 [256,320) PV1 [320,384)
+constexpr int ATTN_THREADS = 320;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnDev {
@@ -43,30 +47,42 @@ __device__ __forceinline__ bool block_active(const uint32_t* mrow, int blk) {
   const uint4 w = *reinterpret_cast<const uint4*>(mrow + blk * 4);
   return (w.x | w.y | w.z | w.w) != 0u;
 }
+__device__ __forceinline__ int next_active(const uint32_t* mrow, int from, int nkb) {
+  for (int j = from; j < nkb; ++j)
+    if (block_active(mrow, j)) return j;
+  return -1;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;                          // [KV_STAGES][16 KB]
-  uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;        // [KV_STAGES][16 KB]
-  uint8_t* sP = sV + KV_STAGES * KV_TILE_BYTES;        // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // 1
-  uint64_t* p_full = bars + 6;        // 1 (128 arrivals)
-  uint64_t* pv_full = bars + 7;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sQ = smem;                                   // [2][16 KB]
+  uint8_t* sK = sQ + 2 * Q_BYTES;                       // [KV_STAGES][16 KB]
+  uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES][16 KB]
+  uint8_t* sP = sV + KV_STAGES * KV_TILE_BYTES;         // [2][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* kv_full = bars + 1;             // [KV_STAGES]
+  uint64_t* kv_empty = kv_full + KV_STAGES; // [KV_STAGES]
+  uint64_t* s_full = kv_empty + KV_STAGES;  // [2]
+  uint64_t* p_full = s_full + 2;            // [2] (128 arrivals each)
+  uint64_t* pv_full = p_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int qblk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qgrp = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int q0 = qgrp * 2 * BQ;                       // first query row of this CTA
+  const int nq = (p.Lq - q0 >= 2 * BQ) ? 2 : 1;       // query tiles handled here
   const int nkb = p.Lk / BKV;
   const uint32_t* mrow =
       p.mask_bits ? p.mask_bits + static_cast<size_t>(b) * p.mask_stride_words : nullptr;
@@ -80,9 +96,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_full[t], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<ATTN_TMEM_COLS>(tmem_slot);
@@ -90,13 +108,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_pv = tmem_base + 128;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(sQ, &tmap_q, q_full, head * HD, b * p.Lq + qblk * BQ);
+      mbar_arrive_expect_tx(q_full, nq * Q_BYTES);
+      for (int t = 0; t < nq; ++t)
+        tma_load_2d(sQ + t * Q_BYTES, &tmap_q, q_full, head * HD, b * p.Lq + q0 + t * BQ);
       int it = 0;
       for (int j = 0; j < nkb; ++j) {
         if (!block_active(mrow, j)) continue;
@@ -113,154 +130,185 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P K-major, V MN-major
-      mbar_wait(q_full, 0);
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
-      int it = 0;
-      for (int j = 0; j < nkb; ++j) {
-        if (!block_active(mrow, j)) continue;
-        const int s = it % KV_STAGES;
-        const uint32_t ph = (it / KV_STAGES) & 1;
-        mbar_wait(&kv_full[s], ph);
-        tc_fence_after_sync();
-        const uint32_t k_addr = smem_u32(sK + s * KV_TILE_BYTES);
-        const uint32_t v_addr = smem_u32(sV + s * KV_TILE_BYTES);
-        // S = Q K^T : 4 k-steps of 16 along head_dim (32 bytes each inside the swizzle atom)
+      // S_t = Q_t K^T : 4 k-steps of 16 along head_dim (32 bytes each inside the swizzle atom)
+      auto issue_s = [&](int t, int stage) {
+        const uint32_t k_addr = smem_u32(sK + stage * KV_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(q_addr + k * 32, 1024, 16);
+          const uint64_t da = make_smem_desc_sw128(q_addr + t * Q_BYTES + k * 32, 1024, 16);
           const uint64_t db = make_smem_desc_sw128(k_addr + k * 32, 1024, 16);
-          umma_bf16(tmem_s, da, db, idesc_s, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + t * 128, da, db, idesc_s, k != 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
-        // wait for softmax to publish P (implies S consumed and previous PV consumed)
-        mbar_wait(p_full, it & 1);
-        tc_fence_after_sync();
-        // PV = P V : 8 k-steps of 16 keys.  P: sub-tile (k/4) of 16 KB, +32 B per step inside.
-        // V (MN-major): 16 keys = 16 rows of 128 B -> +2048 B per step; 8-key groups 1024 B apart.
+        umma_commit(&s_full[t]);
+      };
+      // PV_t = P_t V : 8 k-steps of 16 keys.  P: sub-tile (k/4) of 16 KB, +32 B per step inside.
+      // V (MN-major): 16 keys = 16 rows of 128 B -> +2048 B per step; 8-key groups 1024 B apart.
+      auto issue_pv = [&](int t, int stage) {
+        const uint32_t v_addr = smem_u32(sV + stage * KV_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t da =
-              make_smem_desc_sw128(p_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32, 1024, 16);
+          const uint64_t da = make_smem_desc_sw128(
+              p_addr + t * P_BYTES + (k >> 2) * (BQ * 128) + (k & 3) * 32, 1024, 16);
           const uint64_t db = make_smem_desc_sw128(v_addr + k * 2048, 1024, 16);
-          umma_bf16(tmem_pv, da, db, idesc_pv, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + 256 + t * 64, da, db, idesc_pv, k != 0 ? 1u : 0u);
         }
-        umma_commit(pv_full);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&pv_full[t]);
+      };
+      int jn = next_active(mrow, 0, nkb);
+      int it = 0;
+      if (jn >= 0) {
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after_sync();
+        for (int t = 0; t < nq; ++t) issue_s(t, 0);
+      }
+      while (jn >= 0) {
+        jn = next_active(mrow, jn + 1, nkb);
+        const int stage = it % KV_STAGES;
+        const int nstage = (it + 1) % KV_STAGES;
+        const uint32_t par = it & 1;
+        // ---- tile 0
+        mbar_wait(&p_full[0], par);  // P0 published: S0 consumed, previous PV0 consumed
+        tc_fence_after_sync();
+        issue_pv(0, stage);
+        if (jn >= 0) {
+          mbar_wait(&kv_full[nstage], ((it + 1) / KV_STAGES) & 1);
+          tc_fence_after_sync();
+          issue_s(0, nstage);
+        }
+        // ---- tile 1
+        if (nq == 2) {
+          mbar_wait(&p_full[1], par);
+          tc_fence_after_sync();
+          issue_pv(1, stage);
+        }
+        umma_commit(&kv_empty[stage]);  // K/V of this block are dead once the MMAs above retire
+        if (jn >= 0 && nq == 2) issue_s(1, nstage);
         ++it;
       }
     }
   } else {
-    // ------------------------- softmax / output warps -------------------------
-    const int lg = warp & 3;
-    const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
-    float o[HD];
+    // ------------------------- softmax / output warp groups -------------------------
+    const int tile = (warp - 2) >> 2;  // 0: warps 2..5, 1: warps 6..9
+    if (tile < nq) {
+      const int lg = warp & 3;
+      const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
+      const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
+      const uint32_t tmem_s = tmem_base + tile * 128 + lane_off;
+      const uint32_t tmem_pv = tmem_base + 256 + tile * 64 + lane_off;
+      uint8_t* sPt = sP + tile * P_BYTES;
+      float o[HD];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    uint32_t sreg[32];
-    int it = 0;
-    for (int j = 0; j < nkb; ++j) {
-      if (!block_active(mrow, j)) continue;
-      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      if (mrow != nullptr) {
-        const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
-        mw[0] = w.x; mw[1] = w.y; mw[2] = w.z; mw[3] = w.w;
-      }
-      mbar_wait(s_full, it & 1);
-      tc_fence_after_sync();
-      // pass 1: row max over attendable keys
-      float bmax = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_32x32b_x32(tmem_s + lane_off + c * 32, sreg);
-        tmem_ld_wait();
-        const uint32_t bits = mw[c];
-        if (bits == 0xffffffffu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, __uint_as_float(sreg[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if ((bits >> i) & 1u) bmax = fmaxf(bmax, __uint_as_float(sreg[i]));
+      for (int i = 0; i < HD; ++i) o[i] = 0.f;
+      float m = -INFINITY, l = 0.f;
+      uint32_t sreg[32];
+      int it = 0;
+      for (int j = 0; j < nkb; ++j) {
+        if (!block_active(mrow, j)) continue;
+        uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (mrow != nullptr) {
+          const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
+          mw[0] = w.x; mw[1] = w.y; mw[2] = w.z; mw[3] = w.w;
         }
+        mbar_wait(&s_full[tile], it & 1);
+        tc_fence_after_sync();
+        // pass 1: row max over attendable keys
+        float bmax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_32x32b_x32(tmem_s + c * 32, sreg);
+          tmem_ld_wait();
+          const uint32_t bits = mw[c];
+          if (bits == 0xffffffffu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, __uint_as_float(sreg[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if ((bits >> i) & 1u) bmax = fmaxf(bmax, __uint_as_float(sreg[i]));
+          }
+        }
+        const float m_new = fmaxf(m, bmax);  // finite: an active block has >= 1 attendable key
+        const float alpha = ex2_approx((m - m_new) * LOG2E);
+        if (it > 0) {
+          // fold in the previous block's PV (computed relative to the old max), then rescale
+          mbar_wait(&pv_full[tile], (it - 1) & 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld_32x32b_x32(tmem_pv + c * 32, sreg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(sreg[i]);
+          }
+        }
+        if (!__all_sync(0xffffffffu, alpha == 1.0f)) {
+#pragma unroll
+          for (int i = 0; i < HD; ++i) o[i] *= alpha;
+        }
+        l *= alpha;
+        m = m_new;
+        const float mb = m_new * LOG2E;
+        // pass 2: p = exp(s - m), row sum, bf16 P into swizzled smem (A operand of the PV MMA)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_32x32b_x32(tmem_s + c * 32, sreg);
+          tmem_ld_wait();
+          const uint32_t bits = mw[c];
+          float pv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = ex2_approx(fmaf(__uint_as_float(sreg[i]), LOG2E, -mb));
+            if (bits != 0xffffffffu && !((bits >> i) & 1u)) e = 0.f;
+            pv[i] = e;
+            l += e;
+          }
+          // columns [c*32, c*32+32) -> sub-tile c/2, 16-byte chunks (c&1)*4 .. +3, XOR row&7
+          uint8_t* prow = sPt + (c >> 1) * (BQ * 128) + r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16(pv[8 * q + 0], pv[8 * q + 1]);
+            u.y = pack_bf16(pv[8 * q + 2], pv[8 * q + 3]);
+            u.z = pack_bf16(pv[8 * q + 4], pv[8 * q + 5]);
+            u.w = pack_bf16(pv[8 * q + 6], pv[8 * q + 7]);
+            const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = u;
+          }
+        }
+        fence_proxy_async_smem();  // st.shared -> visible to the tensor core (async proxy)
+        tc_fence_before_sync();    // order our tcgen05.ld of S / PV before the next MMAs
+        mbar_arrive(&p_full[tile]);
+        ++it;
       }
-      const float m_new = fmaxf(m, bmax);  // finite: an active block has >= 1 attendable key
-      const float alpha = exp2f((m - m_new) * LOG2E);
       if (it > 0) {
-        // fold in the previous block's PV (computed relative to the old max), then rescale
-        mbar_wait(pv_full, (it - 1) & 1);
+        mbar_wait(&pv_full[tile], (it - 1) & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          tmem_ld_32x32b_x32(tmem_pv + lane_off + c * 32, sreg);
+          tmem_ld_32x32b_x32(tmem_pv + c * 32, sreg);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(sreg[i]);
         }
       }
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      bf16* orow =
+          p.O + static_cast<size_t>(b * p.Lq + q0 + tile * BQ + r) * p.ldo + head * HD;
+      uint4* o4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-      for (int i = 0; i < HD; ++i) o[i] *= alpha;
-      l *= alpha;
-      m = m_new;
-      const float mb = m_new * LOG2E;
-      // pass 2: p = exp(s - m), row sum, bf16 P into swizzled smem (A operand of the PV MMA)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_32x32b_x32(tmem_s + lane_off + c * 32, sreg);
-        tmem_ld_wait();
-        const uint32_t bits = mw[c];
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(fmaf(__uint_as_float(sreg[i]), LOG2E, -mb));
-          if (bits != 0xffffffffu && !((bits >> i) & 1u)) e = 0.f;
-          pv[i] = e;
-          l += e;
-        }
-        // columns [c*32, c*32+32) -> sub-tile c/2, 16-byte chunks (c&1)*4 .. +3, XOR row&7
-        uint8_t* prow = sP + (c >> 1) * (BQ * 128) + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(pv[8 * q + 0], pv[8 * q + 1]);
-          u.y = pack_bf16(pv[8 * q + 2], pv[8 * q + 3]);
-          u.z = pack_bf16(pv[8 * q + 4], pv[8 * q + 5]);
-          u.w = pack_bf16(pv[8 * q + 6], pv[8 * q + 7]);
-          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = u;
-        }
+      for (int q = 0; q < 8; ++q) {
+        uint4 u;
+        u.x = pack_bf16(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
+        u.y = pack_bf16(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
+        u.z = pack_bf16(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
+        u.w = pack_bf16(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
+        o4[q] = u;
       }
-      fence_proxy_async_smem();  // st.shared -> visible to the tensor core (async proxy)
-      tc_fence_before_sync();    // order our tcgen05.ld of S / PV before the MMA warp's next MMAs
-      mbar_arrive(p_full);
-      ++it;
+      tc_fence_before_sync();
     }
-    if (it > 0) {
-      mbar_wait(pv_full, (it - 1) & 1);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tmem_ld_32x32b_x32(tmem_pv + lane_off + c * 32, sreg);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(sreg[i]);
-      }
-    }
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
-    bf16* orow = p.O + static_cast<size_t>(b * p.Lq + qblk * BQ + r) * p.ldo + head * HD;
-    uint4* o4 = reinterpret_cast<uint4*>(orow);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      uint4 u;
-      u.x = pack_bf16(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
-      u.y = pack_bf16(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
-      u.z = pack_bf16(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
-      u.w = pack_bf16(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
-      o4[q] = u;
-    }
-    tc_fence_before_sync();
   }
   __syncthreads();
   if (warp == 1) {
@@ -299,10 +347,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   AttnDev d;
   d.O = a.O; d.ldo = a.ldo; d.heads = a.heads; d.Lq = a.Lq; d.Lk = a.Lk;
   d.mask_bits = a.mask_bits; d.mask_stride_words = a.mask_stride_words;
-  dim3 grid(a.Lq / BQ, a.heads, a.nbatch);
+  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch);
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
-  attention_tcgen05_kernel<<<grid, 192, ATTN_SMEM, stream>>>(tq, tk, tv, d);
+  attention_tcgen05_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(tq, tk, tv, d);
   MSD_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;
