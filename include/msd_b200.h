@@ -128,6 +128,11 @@ uint64_t msd_launch_count(void);
 int msd_op_dense(const float* a, const float* w, int32_t M, int32_t N, int32_t K, float* out,
                  void* stream);
 
+/* Same, selecting the kernel: variant 0 = CTA-pair persistent kernel (default), 1 = single-CTA
+ * kernel; block_n 0 = auto or one of 64/128/192/256 (192 only with variant 0). */
+int msd_op_dense_variant(const float* a, const float* w, int32_t M, int32_t N, int32_t K,
+                         float* out, int32_t variant, int32_t block_n, void* stream);
+
 /* dot_product_attention (layers.py:109-181) for head_dim 64 with a key-padding mask:
  * q [nb, Lq, heads*64], k/v [nb, Lk, heads*64] f32 device, key_mask [nb, Lk] int32 or NULL,
  * out [nb, Lq, heads*64] f32 device. */

@@ -66,8 +66,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
+static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                        uint64_t ld, uint32_t box_rows, int elem_bytes);
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(out, base, rows, cols, ld, box_rows, 2);
+}
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(out, base, rows, cols, ld, box_rows, 4);
+}
+
+static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                        uint64_t ld, uint32_t box_rows, int elem_bytes) {
   if (g_encode == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -76,14 +88,16 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                 "cuTensorMapEncodeTiled not available from this driver");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  MSD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0,
+  MSD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * elem_bytes) % 16 == 0,
               "tensor map: base/stride must be 16-byte aligned (ld=%llu)", (unsigned long long)ld);
   MSD_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u out of range", box_rows);
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t gstride[1] = {ld * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+  CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        2, const_cast<void*>(base), gdim,
                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -909,6 +923,11 @@ int msd_profile_step(msd_ctx* c, int32_t step_i, int32_t reps, double* out) {
 // ---------------------------------------------------------------------------
 int msd_op_dense(const float* a, const float* w, int32_t M, int32_t N, int32_t K, float* out,
                  void* stream) {
+  return msd_op_dense_variant(a, w, M, N, K, out, 0, 0, stream);
+}
+
+int msd_op_dense_variant(const float* a, const float* w, int32_t M, int32_t N, int32_t K,
+                         float* out, int32_t variant, int32_t block_n, void* stream) {
   MSD_REQUIRE(a && w && out, "msd_op_dense: null argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   TempBufs tb;
@@ -917,7 +936,11 @@ int msd_op_dense(const float* a, const float* w, int32_t M, int32_t N, int32_t K
   MSD_TRY(tb.get(&wb, static_cast<size_t>(N) * K));
   MSD_TRY(launch_f32_to_bf16(a, ab, static_cast<long long>(M) * K, st));
   MSD_TRY(launch_pack_weight(w, K, N, wb, K, 0, 0, 0, st));
-  MSD_TRY(gemm(ab, K, wb, K, M, N, K, EPI_F32, out, N, nullptr, st));
+  GemmArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.A = ab; ga.B = wb; ga.M = M; ga.N = N; ga.K = K; ga.lda = K; ga.ldb = K;
+  ga.epilogue = EPI_F32; ga.out = out; ga.ldo = N; ga.variant = variant; ga.block_n = block_n;
+  MSD_TRY(launch_gemm(ga, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -10,6 +10,8 @@
 //
 // Replaces the XLA dot_general lowering of DenseGeneral (msd/layers.py:397-442) for every
 // projection on the hot path.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -209,6 +211,388 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair persistent GEMM: a 2-CTA cluster owns a 256 x BN output tile (each CTA 128 rows and
+// half of the B tile in its shared memory); the even CTA issues tcgen05.mma.cta_group::2 for
+// both.  Per k-block each CTA pulls 16 KB of A and BN/2 x 128 B of B: half the L2 traffic per
+// FLOP of the 1-CTA kernel above, which ncu showed pinned at the L2 bandwidth cap with the
+// tensor pipe ~30 % active.  Clusters are persistent over tiles; the TMEM accumulator is
+// double-buffered so tile i's epilogue overlaps tile i+1's main loop.
+//   warp 0 (one lane, both CTAs)   TMA producer (own A rows, own half of B), bytes credited to
+//                                  the leader's `full` barrier
+//   warp 1 (one lane, leader)      MMA issuer; commits multicast to both CTAs' barriers
+//   warps 2..5 (both CTAs)         epilogue of the CTA's own 128 accumulator rows
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct PairCfg {
+  static constexpr int HALF_N = BN / 2;
+  static constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  // epilogue staging: O ring 2 x [128 rows x 128 B] (TMA-store source; the bf16 path uses it as
+  // 4 per-warp transpose tiles) + R ring 2 x [128 x 128 B] (TMA-loaded residual chunks)
+  static constexpr int EPI_BYTES = 4 * 16384;
+  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES > 8 ? 8 : (160 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + EPI_BYTES + 512 /*barriers*/ + 1024 /*align*/;
+  static constexpr uint32_t ACC_COLS = BN;  // columns per accumulator buffer
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+};
+
+// ---- coalesced epilogue ---------------------------------------------------------------------
+// tcgen05.ld hands every thread ONE accumulator row; storing rows straight from registers makes
+// each warp-level store touch 32 cache lines.  Instead each epilogue warp transposes its
+// 32 rows x (64 or 128) bytes through a private, XOR-swizzled smem tile so that global loads and
+// stores cover whole 64/128-byte row segments (8 or 4 lanes per row).
+//   stage_write<K16>: thread `lane` (row) writes its K16 16-byte chunks
+//   stage_read <K16>: lane reads chunk (lane % K16) of row (it * (32 / K16) + lane / K16)
+template <int K16>
+__device__ __forceinline__ void stage_write(uint8_t* tile, int lane, const uint4* chunks) {
+#pragma unroll
+  for (int c = 0; c < K16; ++c)
+    *reinterpret_cast<uint4*>(tile + lane * 128 + ((c ^ (lane & 7)) * 16)) = chunks[c];
+}
+template <int K16>
+__device__ __forceinline__ uint4 stage_read(const uint8_t* tile, int lane, int it, int* row_out,
+                                            int* chunk_out) {
+  constexpr int RPI = 32 / K16;  // rows per iteration
+  const int row = it * RPI + lane / K16;
+  const int chunk = lane % K16;
+  *row_out = row;
+  *chunk_out = chunk;
+  return *reinterpret_cast<const uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) * 16));
+}
+
+// fp32 outputs: 32 accumulator columns [col, col+32) of rows [row0, row0+32)
+__device__ __forceinline__ void epilogue_f32_chunk(const GemmDev& p, uint8_t* tile, int lane,
+                                                   int row0, int col, const uint32_t (&r)[32]) {
+  uint4 ch[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) ch[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+  stage_write<8>(tile, lane, ch);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    int rr, cc;
+    const uint4 u = stage_read<8>(tile, lane, it, &rr, &cc);
+    const int row = row0 + rr;
+    if (row >= p.M) continue;
+    float4 v = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
+                           __uint_as_float(u.w));
+    const size_t off = static_cast<size_t>(row) * p.ldo + col + cc * 4;
+    if (p.epilogue == EPI_RESID_F32) {
+      const float4 q = *reinterpret_cast<const float4*>(p.resid + off);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    } else if (p.epilogue == EPI_POS_F32) {
+      const int seq = row / p.pos_rows;
+      int pr = row - seq * p.pos_rows;
+      if (p.pos_shift != nullptr) {
+        pr -= p.pos_shift[seq];
+        if (pr < 0) pr += p.pos_rows;
+      }
+      const float4 q = __ldg(reinterpret_cast<const float4*>(
+          p.pos + static_cast<size_t>(pr) * p.N + col + cc * 4));
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    float* out = reinterpret_cast<float*>(p.out);
+    *reinterpret_cast<float4*>(out + off) = v;
+    if (p.epilogue == EPI_POS_F32 && p.dup_rows > 0)
+      *reinterpret_cast<float4*>(out + off + static_cast<size_t>(p.dup_rows) * p.ldo) = v;
+  }
+  __syncwarp();
+}
+
+// bf16 outputs: K16 16-byte chunks per row (64 or 32 output columns) starting at out column `col`
+template <int K16>
+__device__ __forceinline__ void epilogue_bf16_rows(const GemmDev& p, uint8_t* tile, int lane,
+                                                   int row0, int col, const uint4* chunks) {
+  stage_write<K16>(tile, lane, chunks);
+  __syncwarp();
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+#pragma unroll
+  for (int it = 0; it < K16; ++it) {
+    int rr, cc;
+    const uint4 u = stage_read<K16>(tile, lane, it, &rr, &cc);
+    const int row = row0 + rr;
+    if (row < p.M)
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * p.ldo + col + cc * 8) = u;
+  }
+  __syncwarp();
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                              const __grid_constant__ CUtensorMap tmap_b,
+                              const __grid_constant__ CUtensorMap tmap_out,
+                              const __grid_constant__ CUtensorMap tmap_res, const GemmDev p) {
+  using Cfg = PairCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* sEpi = sB + STAGES * Cfg::B_STAGE_BYTES;  // O ring [2][16 KB] then R ring [2][16 KB]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + Cfg::EPI_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2] (leader's copy is the one used)
+  uint64_t* resid_full_bar = tmem_empty_bar + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_full_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_kb = p.K / BLOCK_K;
+  const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = p.N / BN;
+  const int num_tiles = m_pairs * n_tiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&resid_full_bar[a], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2 && lane == 0 && p.epilogue != EPI_BF16 && p.epilogue != EPI_GATED_GELU) {
+    tma_prefetch_desc(&tmap_out);
+    if (p.epilogue == EPI_RESID_F32) tma_prefetch_desc(&tmap_res);
+  }
+  if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile % m_pairs) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        const int n0 = (tile / m_pairs) * BN + static_cast<int>(rank) * Cfg::HALF_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2sm(sA + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
+          tma_load_2d_2sm(sB + s * Cfg::B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN, 0, 0);
+      int it = 0, tcount = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
+        const int acc = tcount & 1;
+        const uint32_t acc_ph = (tcount >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // both epilogues drained this buffer
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 1024, 16);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 1024, 16);
+            umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[s]);  // frees the slot in BOTH CTAs
+        }
+        umma_commit_2sm(&tmem_full_bar[acc]);  // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, TMEM lane group = warp % 4 ----------------
+    const int lg = warp & 3;
+    uint8_t* tile_smem = sEpi + lg * 4096;
+    uint8_t* sO = sEpi;               // [2][16 KB]
+    uint8_t* sR = sEpi + 2 * 16384;   // [2][16 KB]
+    const bool f32_path = p.epilogue != EPI_BF16 && p.epilogue != EPI_GATED_GELU;
+    const bool has_res = p.epilogue == EPI_RESID_F32;
+    const bool epi_leader = (warp == 2 && lane == 0);
+    constexpr int NCH = BN / 32;
+    uint32_t gc = 0;  // running fp32 chunk counter (ring slot = gc & 1, phase = (gc >> 1) & 1)
+    int tcount = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
+      const int acc = tcount & 1;
+      const uint32_t acc_ph = (tcount >> 1) & 1;
+      const int tile_row = (tile % m_pairs) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+      const int row0 = tile_row + lg * 32;
+      const int n0 = (tile / m_pairs) * BN;
+      if (has_res && epi_leader) {
+        // residual chunks 0 and 1 of this tile travel while the main loop is still running
+#pragma unroll
+        for (int c = 0; c < 2 && c < NCH; ++c) {
+          const uint32_t g = gc + c;
+          mbar_arrive_expect_tx(&resid_full_bar[g & 1], 16384);
+          tma_load_2d(sR + (g & 1) * 16384, &tmap_res, &resid_full_bar[g & 1], n0 + c * 32, tile_row);
+        }
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
+      uint32_t r[32];
+      if (p.epilogue == EPI_GATED_GELU) {
+        uint32_t g[32];
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          tmem_ld_32x32b_x32(t_row + c, r);
+          tmem_ld_32x32b_x32(t_row + c + 32, g);
+          tmem_ld_wait();
+          uint4 ch[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              v[i] = gelu_tanh(__uint_as_float(r[8 * q + i])) * __uint_as_float(g[8 * q + i]);
+            ch[q] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                               pack_bf16(v[6], v[7]));
+          }
+          epilogue_bf16_rows<4>(p, tile_smem, lane, row0, (n0 + c) / 2, ch);
+        }
+      } else if (p.epilogue == EPI_BF16) {
+        uint32_t g[32];
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          tmem_ld_32x32b_x32(t_row + c, r);
+          tmem_ld_32x32b_x32(t_row + c + 32, g);
+          tmem_ld_wait();
+          uint4 ch[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ch[q] = make_uint4(
+                pack_bf16(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1])),
+                pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
+                pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])),
+                pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+            ch[4 + q] = make_uint4(
+                pack_bf16(__uint_as_float(g[8 * q + 0]), __uint_as_float(g[8 * q + 1])),
+                pack_bf16(__uint_as_float(g[8 * q + 2]), __uint_as_float(g[8 * q + 3])),
+                pack_bf16(__uint_as_float(g[8 * q + 4]), __uint_as_float(g[8 * q + 5])),
+                pack_bf16(__uint_as_float(g[8 * q + 6]), __uint_as_float(g[8 * q + 7])));
+          }
+          epilogue_bf16_rows<8>(p, tile_smem, lane, row0, n0 + c, ch);
+        }
+      } else {
+        // fp32 outputs: registers (+ TMA-loaded residual / position rows) -> swizzled smem tile
+        // -> one TMA store per 128 x 32 chunk.  One named barrier per chunk.
+        const int trow = lg * 32 + lane;   // row inside the CTA's 128-row tile
+        const int grow = tile_row + trow;  // global row
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++gc) {
+          const uint32_t slot = gc & 1;
+          tmem_ld_32x32b_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (has_res) {
+            mbar_wait(&resid_full_bar[slot], (gc >> 1) & 1);
+            const uint8_t* rrow = sR + slot * 16384 + trow * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 f = *reinterpret_cast<const float4*>(rrow + ((q ^ (trow & 7)) * 16));
+              v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+            }
+          } else if (p.epilogue == EPI_POS_F32 && grow < p.M) {
+            const int seq = grow / p.pos_rows;
+            int pr = grow - seq * p.pos_rows;
+            if (p.pos_shift != nullptr) {
+              pr -= p.pos_shift[seq];
+              if (pr < 0) pr += p.pos_rows;
+            }
+            const float4* ps = reinterpret_cast<const float4*>(
+                p.pos + static_cast<size_t>(pr) * p.N + n0 + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 f = __ldg(ps + q);
+              v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+            }
+          }
+          uint8_t* orow = sO + slot * 16384 + trow * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(orow + ((q ^ (trow & 7)) * 16)) =
+                make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          fence_proxy_async_smem();
+          // the store that last read the OTHER O slot must be done before anyone rewrites it
+          if (epi_leader) tma_store_wait_read<0>();
+          named_barrier_sync(1, 128);
+          if (epi_leader) {
+            if (tile_row < p.M) {  // M % 128 == 0: a CTA's rows are all valid or all padding
+              tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row);
+              if (p.epilogue == EPI_POS_F32 && p.dup_rows > 0)
+                tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row + p.dup_rows);
+            }
+            tma_store_commit();
+            if (has_res && c + 2 < NCH) {
+              mbar_arrive_expect_tx(&resid_full_bar[slot], 16384);
+              tma_load_2d(sR + slot * 16384, &tmap_res, &resid_full_bar[slot], n0 + (c + 2) * 32,
+                          tile_row);
+            }
+          }
+        }
+      }
+      // accumulator drained: let the leader's MMA warp reuse it
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+    }
+  }
+  if (warp == 2 && lane == 0) tma_store_wait_all();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                const CUtensorMap& tres, const GemmDev& d, cudaStream_t st) {
+  using Cfg = PairCfg<BN>;
+  const int m_pairs = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_tiles = m_pairs * (d.N / BN);
+  int sms = 148;
+  const int clusters = num_tiles < sms / 2 ? num_tiles : sms / 2;
+  ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
+                 2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
+                     4.0 * d.M * d.N, st);
+  gemm_bf16_tcgen05_pair_kernel<BN><<<2 * clusters, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, d);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+template <int BN>
+int configure_pair() {
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<BN>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PairCfg<BN>::SMEM_BYTES));
+  return 0;
+}
+
 template <int BN>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
@@ -235,7 +619,28 @@ int configure_bn() {
 int gemm_configure() {
   if (int rc = configure_bn<64>()) return rc;
   if (int rc = configure_bn<128>()) return rc;
-  return configure_bn<256>();
+  if (int rc = configure_bn<256>()) return rc;
+  if (int rc = configure_pair<64>()) return rc;
+  if (int rc = configure_pair<128>()) return rc;
+  if (int rc = configure_pair<192>()) return rc;
+  return configure_pair<256>();
+}
+
+// Tile width of the CTA-pair kernel: minimise (waves x per-tile MMA time) over the widths that
+// divide N.  74 clusters run concurrently; a tile costs ~BN cycles per k-step.
+int gemm_pick_pair_bn(int M, int N) {
+  const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int cands[4] = {256, 192, 128, 64};
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    if (N % bn) continue;
+    const int tiles = m_pairs * (N / bn);
+    const int waves = (tiles + 73) / 74;
+    const double cost = static_cast<double>(waves) * (bn + 24);  // +24: per-tile fixed overhead
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 int gemm_pick_block_n(int M, int N) {
@@ -253,11 +658,16 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   MSD_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   MSD_REQUIRE(a.K % BLOCK_K == 0, "gemm: K=%d must be a multiple of %d", a.K, BLOCK_K);
   MSD_REQUIRE(a.M % BLOCK_M == 0, "gemm: M=%d must be a multiple of %d", a.M, BLOCK_M);
-  int bn = a.block_n ? a.block_n : gemm_pick_block_n(a.M, a.N);
-  MSD_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: N=%d has no valid tile width", a.N);
+  static const int forced_variant = [] {
+    const char* e = getenv("MSD_GEMM_VARIANT");  // debugging aid: 1 forces the single-CTA kernel
+    return e ? atoi(e) : 0;
+  }();
+  const bool pair = (forced_variant ? forced_variant : a.variant) != 1;
+  int bn = a.block_n ? a.block_n
+                     : (pair ? gemm_pick_pair_bn(a.M, a.N) : gemm_pick_block_n(a.M, a.N));
+  MSD_REQUIRE(bn == 64 || bn == 128 || bn == 256 || (pair && bn == 192),
+              "gemm: N=%d has no valid tile width", a.N);
   MSD_REQUIRE(a.N % bn == 0, "gemm: N=%d not a multiple of block_n=%d", a.N, bn);
-  if (a.epilogue == EPI_GATED_GELU)
-    MSD_REQUIRE(bn >= 64, "gemm: gated epilogue needs block_n >= 64");
   MSD_REQUIRE(a.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", a.ldo);
 
   CUtensorMap ta, tb;
@@ -268,7 +678,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   if (a.tmap_b) {
     tb = *a.tmap_b;
-  } else if (int rc = make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, bn)) {
+  } else if (int rc = make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, pair ? bn / 2 : bn)) {
     return rc;
   }
   GemmDev d;
@@ -277,6 +687,21 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.out = a.out; d.ldo = a.ldo;
   d.resid = a.resid; d.pos = a.pos; d.pos_rows = a.pos_rows > 0 ? a.pos_rows : 1;
   d.pos_shift = a.pos_shift; d.dup_rows = a.dup_rows;
+  if (pair) {
+    CUtensorMap tout = ta, tres = ta;  // placeholders unless the epilogue is an fp32 one
+    if (a.epilogue != EPI_BF16 && a.epilogue != EPI_GATED_GELU) {
+      const int rows = a.M + (a.epilogue == EPI_POS_F32 ? a.dup_rows : 0);
+      if (int rc = make_tmap_f32_2d(&tout, a.out, rows, a.N, a.ldo, BLOCK_M)) return rc;
+      if (a.epilogue == EPI_RESID_F32)
+        if (int rc = make_tmap_f32_2d(&tres, a.resid, a.M, a.N, a.ldo, BLOCK_M)) return rc;
+    }
+    switch (bn) {
+      case 64: return launch_pair<64>(ta, tb, tout, tres, d, stream);
+      case 128: return launch_pair<128>(ta, tb, tout, tres, d, stream);
+      case 192: return launch_pair<192>(ta, tb, tout, tres, d, stream);
+      default: return launch_pair<256>(ta, tb, tout, tres, d, stream);
+    }
+  }
   switch (bn) {
     case 64: return launch_bn<64>(ta, tb, d, stream);
     case 128: return launch_bn<128>(ta, tb, d, stream);

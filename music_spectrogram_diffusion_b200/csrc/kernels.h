@@ -42,6 +42,9 @@ struct ProfScope {
 // box = [box_rows, 64 cols] (128-byte inner extent), SWIZZLE_128B.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows);
+// Same for fp32 with box = [box_rows, 32 cols] (128-byte inner extent), SWIZZLE_128B.
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t ld, uint32_t box_rows);
 
 // ---------------------------------------------------------------------------
 // GEMM: D[M,N] = A[M,K] * B[N,K]^T, bf16 operands (both K-major), fp32 accumulate
@@ -72,12 +75,14 @@ struct GemmArgs {
   // Pre-built tensor maps (engine caches them); when null the launcher builds them.
   const CUtensorMap* tmap_a;
   const CUtensorMap* tmap_b;
-  int block_n;           // 0 = auto (64/128/256)
+  int block_n;           // 0 = auto
+  int variant;           // 0 = CTA-pair persistent kernel (default), 1 = single-CTA kernel
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 int gemm_configure();  // opt in to the kernels' dynamic shared memory sizes (idempotent)
 // Box rows the A / B maps must be built with for a given block_n choice.
 int gemm_pick_block_n(int M, int N);
+int gemm_pick_pair_bn(int M, int N);
 
 // ---------------------------------------------------------------------------
 // Attention: O = softmax(Q K^T + keymask) V, no 1/sqrt(d), head_dim 64.

@@ -168,13 +168,14 @@ def launch_count() -> int:
 
 
 # ---- operator-level hooks (unit parity with msd/layers.py) --------------------
-def op_dense(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+def op_dense(a: torch.Tensor, w: torch.Tensor, variant: int = 0, block_n: int = 0) -> torch.Tensor:
   lib = _native.load()
   m, k = a.shape
   n = w.shape[1]
   out = torch.empty(m, n, dtype=torch.float32, device=a.device)
-  _native.check(lib.msd_op_dense(_ptr(a.contiguous()), _ptr(w.contiguous()), m, n, k, _ptr(out),
-                                 _stream(a.device)), 'msd_op_dense')
+  _native.check(lib.msd_op_dense_variant(_ptr(a.contiguous()), _ptr(w.contiguous()), m, n, k,
+                                         _ptr(out), variant, block_n, _stream(a.device)),
+                'msd_op_dense_variant')
   return out
 
 

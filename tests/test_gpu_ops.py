@@ -11,14 +11,18 @@ from tests.helpers import bf16_round
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 384, 128), (512, 2304, 768),
-                                   (128, 64, 384), (384, 256, 2048)])
-def test_dense_general(cuda_device, M, N, K):
+@pytest.mark.parametrize('variant,block_n', [(0, 0), (0, 64), (0, 128), (0, 192), (0, 256),
+                                             (1, 0), (1, 64), (1, 128), (1, 256)])
+@pytest.mark.parametrize('M,N,K', [(128, 768, 64), (256, 768, 128), (512, 2304, 768),
+                                   (384, 768, 384), (2048 + 128, 1536, 2048)])
+def test_dense_general(cuda_device, M, N, K, variant, block_n):
   from music_spectrogram_diffusion_b200 import engine
+  if block_n and N % block_n:
+    pytest.skip('tile width does not divide N')
   g = torch.Generator().manual_seed(M + N + K)
   a = bf16_round(torch.randn(M, K, generator=g))
   w = bf16_round(torch.randn(K, N, generator=g) / np.sqrt(K))
-  got = engine.op_dense(a.to(cuda_device), w.to(cuda_device)).cpu()
+  got = engine.op_dense(a.to(cuda_device), w.to(cuda_device), variant, block_n).cpu()
   want = O.dense_general(a.double(), w.double()).float()
   err = (got - want).abs().max().item()
   assert err < 2e-4 * np.sqrt(K), f'max err {err}'

@@ -23,13 +23,14 @@ def report(name, got, want, tol):
       print('    bad rows (first 20):', rows[:20].tolist(), ' n=', len(rows))
       print('    bad cols (first 20):', cols[:20].tolist(), ' n=', len(cols))
 
-def probe_gemm():
-  for (M, N, K) in [(128, 64, 64), (128, 128, 64), (128, 128, 128), (256, 256, 256), (128, 256, 768)]:
+def probe_gemm(variant=0):
+  print('--- gemm variant', variant)
+  for (M, N, K) in [(128, 64, 64), (256, 128, 64), (256, 192, 128), (256, 256, 256), (128, 256, 768), (1024, 768, 768), (4096, 2304, 768)]:
     # selection probe: A one-hot -> out[m, n] = W[m % K, n]
     a = torch.zeros(M, K); a[torch.arange(M), torch.arange(M) % K] = 1.0
     w = ((torch.arange(K)[:, None] + 2 * torch.arange(N)[None, :]) % 251).float()
     try:
-      got = engine.op_dense(a.to(dev), w.to(dev)).cpu()
+      got = engine.op_dense(a.to(dev), w.to(dev), variant).cpu()
       report(f'gemm-select {M}x{N}x{K}', got, w[torch.arange(M) % K], 0.5)
     except Exception as e:
       print('gemm-select', (M, N, K), 'EXC', e)
@@ -38,7 +39,7 @@ def probe_gemm():
     a = torch.randn(M, K, generator=g).bfloat16().float()
     w = (torch.randn(K, N, generator=g) / np.sqrt(K)).bfloat16().float()
     try:
-      got = engine.op_dense(a.to(dev), w.to(dev)).cpu()
+      got = engine.op_dense(a.to(dev), w.to(dev), variant).cpu()
       report(f'gemm-rand {M}x{N}x{K}', got, a @ w, 1e-2)
     except Exception as e:
       print('gemm-rand', (M, N, K), 'EXC', e)
@@ -86,6 +87,7 @@ def probe_attn():
 if __name__ == '__main__':
   _native.load()
   print(torch.cuda.get_device_name(0))
-  ok = probe_gemm()
-  if ok:
+  ok = probe_gemm(0)
+  if '--all' in sys.argv:
+    probe_gemm(1)
     probe_attn()
