@@ -133,6 +133,12 @@ int msd_op_dense(const float* a, const float* w, int32_t M, int32_t N, int32_t K
 int msd_op_dense_variant(const float* a, const float* w, int32_t M, int32_t N, int32_t K,
                          float* out, int32_t variant, int32_t block_n, void* stream);
 
+/* Micro-benchmark hook: average milliseconds of `iters` back-to-back launches of the bf16 GEMM
+ * [M,K] x [N,K]^T with the given epilogue (0 bf16, 1 f32, 2 f32 + residual, 3 gated-GELU) on
+ * zero-filled scratch buffers. */
+int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t variant,
+                   int32_t block_n, int32_t iters, float* ms_out);
+
 /* dot_product_attention (layers.py:109-181) for head_dim 64 with a key-padding mask:
  * q [nb, Lq, heads*64], k/v [nb, Lk, heads*64] f32 device, key_mask [nb, Lk] int32 or NULL,
  * out [nb, Lq, heads*64] f32 device. */

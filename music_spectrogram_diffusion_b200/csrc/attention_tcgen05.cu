@@ -109,8 +109,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  griddep_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
+      griddep_wait();
       mbar_arrive_expect_tx(q_full, nq * Q_BYTES);
       for (int t = 0; t < nq; ++t)
         tma_load_2d(sQ + t * Q_BYTES, &tmap_q, q_full, head * HD, b * p.Lq + q0 + t * BQ);
@@ -156,6 +158,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         umma_commit(&pv_full[t]);
       };
+      griddep_wait();  // mask words may come from the previous kernel
       int jn = next_active(mrow, 0, nkb);
       int it = 0;
       if (jn >= 0) {
@@ -192,6 +195,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   } else {
     // ------------------------- softmax / output warp groups -------------------------
     const int tile = (warp - 2) >> 2;  // 0: warps 2..5, 1: warps 6..9
+    griddep_wait();  // mask words are read and O is written by these warps
     if (tile < nq) {
       const int lg = warp & 3;
       const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
@@ -350,8 +354,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch);
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
-  attention_tcgen05_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(tq, tk, tv, d);
-  MSD_CUDA_CHECK(cudaGetLastError());
+  MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, stream,
+                               tq, tk, tv, d));
   ++g_launch_count;
   return 0;
 }

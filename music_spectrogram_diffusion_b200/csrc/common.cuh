@@ -57,6 +57,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel lets its successor's CTAs be scheduled as
+// SMs free up (launch_dependents at entry) and orders its own global-memory traffic after the
+// predecessor's completion (wait).  Threads that never touch dependent memory may skip wait.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

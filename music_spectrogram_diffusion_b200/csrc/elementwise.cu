@@ -41,9 +41,11 @@ struct NormDev {
 constexpr int NORM_MAX_ITERS = 8;  // d <= 1024
 
 __global__ void __launch_bounds__(256) rmsnorm_film_kernel(const NormDev p) {
+  griddep_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= p.rows) return;
+  griddep_wait();
   const int iters = p.d >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(warp) * p.d);
   float4 v[NORM_MAX_ITERS];
@@ -159,9 +161,11 @@ __device__ __forceinline__ void store_split4(bf16* zs, long long idx, int n_dims
 // One reverse-diffusion update (CFG combine + x0 + clip + DDPM/DDIM mean + noise)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) {
+  griddep_launch_dependents();
   const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long idx = i4 * 4;
   if (idx >= a.n) return;
+  griddep_wait();
   const int step = *a.step;
   const float* cf = a.coef + static_cast<size_t>(step) * 8;
   const float x0_scale = cf[0], eps_scale = cf[1], c_z = cf[2], c_x0 = cf[3], sigma = cf[4];
@@ -209,7 +213,11 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) 
   }
 }
 
-__global__ void step_advance_kernel(int* step) { *step -= 1; }
+__global__ void step_advance_kernel(int* step) {
+  griddep_launch_dependents();
+  griddep_wait();
+  *step -= 1;
+}
 
 __global__ void __launch_bounds__(256)
 init_z_kernel(const float* init_z, float* z, bf16* zs, long long n, int n_dims,
@@ -396,8 +404,7 @@ int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* ou
   p.rows = rows; p.d = d; p.ldo = ldo; p.split3 = split3;
   p.src_len = 0; p.dst_len = 0; p.dst_off = 0;
   ProfScope prof(KC_NORM, 0.0, static_cast<double>(rows) * d * (4.0 + (split3 ? 6.0 : 2.0)), stream);
-  rmsnorm_film_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(p);
-  MSD_CUDA_CHECK(cudaGetLastError());
+  MSD_CUDA_CHECK(launch_kernel(rmsnorm_film_kernel, dim3(blocks_for(rows, 8)), dim3(256), 0, stream, p));
   ++g_launch_count;
   return 0;
 }
@@ -410,8 +417,7 @@ int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src
   p.film_step_stride = 0; p.film_offset = 0;
   p.rows = B * src_len; p.d = d; p.ldo = d; p.split3 = 0;
   p.src_len = src_len; p.dst_len = dst_len; p.dst_off = dst_off;
-  rmsnorm_film_kernel<<<blocks_for(p.rows, 8), 256, 0, stream>>>(p);
-  MSD_CUDA_CHECK(cudaGetLastError());
+  MSD_CUDA_CHECK(launch_kernel(rmsnorm_film_kernel, dim3(blocks_for(p.rows, 8)), dim3(256), 0, stream, p));
   ++g_launch_count;
   return 0;
 }
@@ -419,16 +425,14 @@ int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src
 int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream) {
   MSD_REQUIRE(a.n % 4 == 0 && a.n_dims % 4 == 0, "sampler: sizes must be multiples of 4");
   ProfScope prof(KC_SAMPLER, 0.0, static_cast<double>(a.n) * (4.0 * (a.passes + 3) + 6.0), stream);
-  sampler_step_kernel<<<blocks_for(a.n / 4, 256), 256, 0, stream>>>(a);
-  MSD_CUDA_CHECK(cudaGetLastError());
+  MSD_CUDA_CHECK(launch_kernel(sampler_step_kernel, dim3(blocks_for(a.n / 4, 256)), dim3(256), 0, stream, a));
   ++g_launch_count;
   return 0;
 }
 
 int launch_step_advance(int* step, cudaStream_t stream) {
   ProfScope prof(KC_OTHER, 0.0, 8.0, stream);
-  step_advance_kernel<<<1, 1, 0, stream>>>(step);
-  MSD_CUDA_CHECK(cudaGetLastError());
+  MSD_CUDA_CHECK(launch_kernel(step_advance_kernel, dim3(1), dim3(1), 0, stream, step));
   ++g_launch_count;
   return 0;
 }

@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -47,6 +48,10 @@ struct ProfRecorder {
   std::vector<Rec> recs;
 };
 ProfRecorder* g_prof = nullptr;
+bool g_use_pdl = [] {
+  const char* v = getenv("MSD_PDL");
+  return !(v && v[0] == '0');
+}();
 void prof_begin(int cls, double flops, double bytes, cudaStream_t st) {
   ProfRecorder::Rec r;
   r.cls = cls; r.flops = flops; r.bytes = bytes;
@@ -942,6 +947,46 @@ int msd_op_dense_variant(const float* a, const float* w, int32_t M, int32_t N, i
   ga.epilogue = EPI_F32; ga.out = out; ga.ldo = N; ga.variant = variant; ga.block_n = block_n;
   MSD_TRY(launch_gemm(ga, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t variant,
+                   int32_t block_n, int32_t iters, float* ms_out) {
+  MSD_REQUIRE(ms_out && iters > 0, "msd_bench_gemm: bad argument");
+  TempBufs tb;
+  bf16 *a = nullptr, *b = nullptr;
+  float *o = nullptr, *r = nullptr;
+  MSD_TRY(tb.get(&a, static_cast<size_t>(M) * K));
+  MSD_TRY(tb.get(&b, static_cast<size_t>(N) * K));
+  MSD_TRY(tb.get(&o, static_cast<size_t>(M) * N));
+  MSD_TRY(tb.get(&r, static_cast<size_t>(M) * N));
+  MSD_CUDA_CHECK(cudaMemset(a, 0, static_cast<size_t>(M) * K * 2));
+  MSD_CUDA_CHECK(cudaMemset(b, 0, static_cast<size_t>(N) * K * 2));
+  MSD_CUDA_CHECK(cudaMemset(r, 0, static_cast<size_t>(M) * N * 4));
+  GemmArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.A = a; ga.B = b; ga.M = M; ga.N = N; ga.K = K; ga.lda = K; ga.ldb = K;
+  ga.epilogue = epilogue; ga.out = o; ga.ldo = (epilogue == EPI_GATED_GELU) ? N / 2 : N;
+  ga.resid = r; ga.variant = variant; ga.block_n = block_n;
+  cudaStream_t st = nullptr;
+  MSD_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = 0;
+  for (int i = 0; i < 3 && rc == 0; ++i) rc = launch_gemm(ga, st);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters && rc == 0; ++i) rc = launch_gemm(ga, st);
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(st);
+  if (rc != 0) return rc;
+  MSD_CUDA_CHECK(e);
   return 0;
 }
 

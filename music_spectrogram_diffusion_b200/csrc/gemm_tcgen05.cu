@@ -97,8 +97,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  griddep_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
+      griddep_wait();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -132,6 +134,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ---------------- epilogue: 4 warps, TMEM lane group = warp % 4 ----------------
     const int lg = warp & 3;
     const int row = m0 + lg * 32 + lane;
+    griddep_wait();
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after_sync();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
@@ -376,15 +379,32 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  griddep_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      // The weight (B) tiles do not depend on the previous kernel: the first ring-full of them
+      // is requested BEFORE griddepcontrol.wait so the fetch overlaps the predecessor's tail.
+      int prefetched = 0;
+      if (cluster_id < num_tiles) {
+        const int n0 = (cluster_id / m_pairs) * BN + static_cast<int>(rank) * Cfg::HALF_N;
+        prefetched = num_kb < STAGES ? num_kb : STAGES;
+        for (int kb = 0; kb < prefetched; ++kb) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[kb], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2sm(sB + kb * Cfg::B_STAGE_BYTES, &tmap_b, &full_bar[kb], kb * BLOCK_K, n0);
+        }
+      }
+      griddep_wait();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile % m_pairs) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         const int n0 = (tile / m_pairs) * BN + static_cast<int>(rank) * Cfg::HALF_N;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
+          if (it < prefetched) {  // slot was armed and its B tile requested above
+            tma_load_2d_2sm(sA + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
+            continue;
+          }
           mbar_wait(&empty_bar[s], ph ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
           tma_load_2d_2sm(sA + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
@@ -432,6 +452,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     constexpr int NCH = BN / 32;
     uint32_t gc = 0;  // running fp32 chunk counter (ring slot = gc & 1, phase = (gc >> 1) & 1)
     int tcount = 0;
+    griddep_wait();  // residual reads / output writes come after the predecessor is complete
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
       const int acc = tcount & 1;
       const uint32_t acc_ph = (tcount >> 1) & 1;
@@ -579,8 +600,8 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
                  2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
                      4.0 * d.M * d.N, st);
-  gemm_bf16_tcgen05_pair_kernel<BN><<<2 * clusters, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, d);
-  MSD_CUDA_CHECK(cudaGetLastError());
+  MSD_CUDA_CHECK(launch_kernel(gemm_bf16_tcgen05_pair_kernel<BN>, dim3(2 * clusters), dim3(192),
+                               Cfg::SMEM_BYTES, st, ta, tb, tout, tres, d));
   ++g_launch_count;
   return 0;
 }
@@ -600,8 +621,8 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, cu
   ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
                  2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
                      4.0 * d.M * d.N, st);
-  gemm_bf16_tcgen05_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, d);
-  MSD_CUDA_CHECK(cudaGetLastError());
+  MSD_CUDA_CHECK(launch_kernel(gemm_bf16_tcgen05_kernel<BN>, grid, dim3(192), Cfg::SMEM_BYTES, st, ta,
+                               tb, d));
   ++g_launch_count;
   return 0;
 }
@@ -629,18 +650,18 @@ int gemm_configure() {
 // Tile width of the CTA-pair kernel: minimise (waves x per-tile MMA time) over the widths that
 // divide N.  74 clusters run concurrently; a tile costs ~BN cycles per k-step.
 int gemm_pick_pair_bn(int M, int N) {
+  // Measured on B200 (tools/gemm_bench.py): the widest tile wins (least L2->SM traffic per FLOP)
+  // unless it leaves clusters idle that a 192-wide tiling would use.
   const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  const int cands[4] = {256, 192, 128, 64};
-  int best = 0;
-  double best_cost = 1e30;
-  for (int bn : cands) {
-    if (N % bn) continue;
-    const int tiles = m_pairs * (N / bn);
-    const int waves = (tiles + 73) / 74;
-    const double cost = static_cast<double>(waves) * (bn + 24);  // +24: per-tile fixed overhead
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+  if (N % 256 == 0) {
+    const int t256 = m_pairs * (N / 256);
+    if (N % 192 == 0 && t256 < 74 && m_pairs * (N / 192) > t256) return 192;
+    return 256;
   }
-  return best;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 0;
 }
 
 int gemm_pick_block_n(int M, int N) {

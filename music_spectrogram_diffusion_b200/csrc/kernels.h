@@ -36,6 +36,27 @@ struct ProfScope {
 };
 
 // ---------------------------------------------------------------------------
+// Launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute when
+// PDL is enabled (default; MSD_PDL=0 disables).  Works under stream capture (programmatic edges).
+// ---------------------------------------------------------------------------
+extern bool g_use_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // TMA tensor maps (driver entry point fetched at run time; no libcuda link).
 // ---------------------------------------------------------------------------
 // 2D row-major bf16 matrix [rows, cols] with leading dimension ld (elements);
