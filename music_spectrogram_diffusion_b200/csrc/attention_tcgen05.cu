@@ -6,14 +6,17 @@
 // One CTA per (256-query group, head, batch row): TWO 128-query tiles ping-pong so that the
 // tensor core works on one tile while the other tile's softmax runs (the exp throughput of the
 // SFU, not the tensor core, bounds head_dim-64 attention on this part).
-//   warp 0 (one lane)   TMA producer: both Q tiles once, then K/V 128-key tiles into a ring
-//   warp 1 (one lane)   MMA issuer:   S_t = Q_t K^T  (M128 x N128 x K64, both operands K-major)
+//   warp 8 (one lane)   TMA producer: both Q tiles once, then K/V 128-key tiles into a ring
+//   warp 9 (one lane)   MMA issuer:   S_t = Q_t K^T  (M128 x N128 x K64, both operands K-major)
 //                                     PV_t = P_t V   (M128 x N64 x K128, P K-major from smem,
 //                                                     V MN-major straight from its [key,64] tile)
-//   warps 2..5 / 6..9   softmax group of tile 0 / tile 1: thread = query row; S read from TMEM
-//                       (tcgen05.ld), online max / exp2 / sum in fp32, P written to smem as bf16
-//                       in the 128B-swizzled K-major layout, PV partials pulled from TMEM and
-//                       accumulated (with the running rescale) in registers
+//   warps 0..3 / 4..7   softmax group of tile 0 / tile 1 (setmaxnreg gives them the registers): thread = query row; the 128 logits of a
+//                       key block are read ONCE from TMEM into registers, max / exp2 / sum in
+//                       fp32, P written to smem as bf16 in the 128B-swizzled K-major layout.
+//                       O accumulates in TMEM across key blocks (MMA accumulate); the running
+//                       max is only raised when it grows by > 2^8 (lazy rescale: then O is
+//                       rescaled in TMEM with tcgen05.ld/st), exact because the final division
+//                       uses the same reference max for numerator and denominator
 // Key blocks whose 128 mask bits are all zero are skipped by every role.
 #include "common.cuh"
 #include "kernels.h"
@@ -31,7 +34,7 @@ constexpr int KV_STAGES = 3;
 constexpr int P_BYTES = BQ * BKV * 2;  // 32 KB per tile (two [128 x 64] swizzled sub-tiles)
 constexpr int ATTN_SMEM = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES + 256 + 1024;
 constexpr uint32_t ATTN_TMEM_COLS = 512;  // S0 [0,128) S1 [128,256) PV0 [256,320) PV1 [320,384)
-constexpr int ATTN_THREADS = 320;
+constexpr int ATTN_THREADS = 384;  // warps 0-3 / 4-7 softmax tile 0 / 1, 8 TMA, 9 MMA, 10-11 idle
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnDev {
@@ -58,6 +61,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Packed fp32x2 arithmetic (sm_100): halves the FMA-pipe instruction count of the softmax.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          const __grid_constant__ CUtensorMap tmap_k,
@@ -76,7 +99,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint64_t* s_full = kv_empty + KV_STAGES;  // [2]
   uint64_t* p_full = s_full + 2;            // [2] (128 arrivals each)
   uint64_t* pv_full = p_full + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
+  uint64_t* s_free = pv_full + 2;           // [2] (128 arrivals: logits copied to registers)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -87,7 +111,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t* mrow =
       p.mask_bits ? p.mask_bits + static_cast<size_t>(b) * p.mask_stride_words : nullptr;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
@@ -100,17 +124,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 128);
       mbar_init(&pv_full[t], 1);
+      mbar_init(&s_free[t], 128);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<ATTN_TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<ATTN_TMEM_COLS>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   griddep_launch_dependents();
-  if (warp == 0) {
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 8) {
     if (lane == 0) {
       griddep_wait();
       mbar_arrive_expect_tx(q_full, nq * Q_BYTES);
@@ -128,7 +155,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         ++it;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P K-major, V MN-major
@@ -147,14 +174,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       };
       // PV_t = P_t V : 8 k-steps of 16 keys.  P: sub-tile (k/4) of 16 KB, +32 B per step inside.
       // V (MN-major): 16 keys = 16 rows of 128 B -> +2048 B per step; 8-key groups 1024 B apart.
-      auto issue_pv = [&](int t, int stage) {
+      auto issue_pv = [&](int t, int stage, int first_block) {
         const uint32_t v_addr = smem_u32(sV + stage * KV_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t da = make_smem_desc_sw128(
               p_addr + t * P_BYTES + (k >> 2) * (BQ * 128) + (k & 3) * 32, 1024, 16);
           const uint64_t db = make_smem_desc_sw128(v_addr + k * 2048, 1024, 16);
-          umma_bf16(tmem_base + 256 + t * 64, da, db, idesc_pv, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + 256 + t * 64, da, db, idesc_pv, (k != 0 || !first_block) ? 1u : 0u);
         }
         umma_commit(&pv_full[t]);
       };
@@ -172,29 +199,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int stage = it % KV_STAGES;
         const int nstage = (it + 1) % KV_STAGES;
         const uint32_t par = it & 1;
-        // ---- tile 0
-        mbar_wait(&p_full[0], par);  // P0 published: S0 consumed, previous PV0 consumed
-        tc_fence_after_sync();
-        issue_pv(0, stage);
+        // Next block's logits first: they only need the S buffer back (s_free), not P, so the
+        // softmax groups never wait for the tensor core in steady state.
         if (jn >= 0) {
           mbar_wait(&kv_full[nstage], ((it + 1) / KV_STAGES) & 1);
-          tc_fence_after_sync();
-          issue_s(0, nstage);
+          for (int t = 0; t < nq; ++t) {
+            mbar_wait(&s_free[t], par);
+            tc_fence_after_sync();
+            issue_s(t, nstage);
+          }
         }
-        // ---- tile 1
-        if (nq == 2) {
-          mbar_wait(&p_full[1], par);
+        for (int t = 0; t < nq; ++t) {
+          mbar_wait(&p_full[t], par);  // P_t published; previous PV_t consumed / rescaled
           tc_fence_after_sync();
-          issue_pv(1, stage);
+          issue_pv(t, stage, it == 0);
         }
         umma_commit(&kv_empty[stage]);  // K/V of this block are dead once the MMAs above retire
-        if (jn >= 0 && nq == 2) issue_s(1, nstage);
         ++it;
       }
     }
+  }
   } else {
     // ------------------------- softmax / output warp groups -------------------------
-    const int tile = (warp - 2) >> 2;  // 0: warps 2..5, 1: warps 6..9
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int tile = warp >> 2;  // 0: warps 0..3, 1: warps 4..7
     griddep_wait();  // mask words are read and O is written by these warps
     if (tile < nq) {
       const int lg = warp & 3;
@@ -203,11 +231,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const uint32_t tmem_s = tmem_base + tile * 128 + lane_off;
       const uint32_t tmem_pv = tmem_base + 256 + tile * 64 + lane_off;
       uint8_t* sPt = sP + tile * P_BYTES;
-      float o[HD];
-#pragma unroll
-      for (int i = 0; i < HD; ++i) o[i] = 0.f;
-      float m = -INFINITY, l = 0.f;
-      uint32_t sreg[32];
+      float m = -INFINITY, l = 0.f;  // reference max (natural units) and running sum
+      uint32_t s[4][32];
+      constexpr float RESCALE_THRESHOLD = 5.545177444f;  // 8 * ln 2: P stays below 2^8
       int it = 0;
       for (int j = 0; j < nkb; ++j) {
         if (!block_active(mrow, j)) continue;
@@ -218,85 +244,114 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         mbar_wait(&s_full[tile], it & 1);
         tc_fence_after_sync();
-        // pass 1: row max over attendable keys
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + c * 32, s[c]);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&s_free[tile]);  // the S buffer may be overwritten by the next block's QK^T
+        // row max over attendable keys (finite: an active block has >= 1 attendable key)
         float bmax = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          tmem_ld_32x32b_x32(tmem_s + c * 32, sreg);
-          tmem_ld_wait();
           const uint32_t bits = mw[c];
           if (bits == 0xffffffffu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, __uint_as_float(sreg[i]));
+            for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, __uint_as_float(s[c][i]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if ((bits >> i) & 1u) bmax = fmaxf(bmax, __uint_as_float(sreg[i]));
+              if ((bits >> i) & 1u) bmax = fmaxf(bmax, __uint_as_float(s[c][i]));
           }
         }
-        const float m_new = fmaxf(m, bmax);  // finite: an active block has >= 1 attendable key
-        const float alpha = ex2_approx((m - m_new) * LOG2E);
-        if (it > 0) {
-          // fold in the previous block's PV (computed relative to the old max), then rescale
-          mbar_wait(&pv_full[tile], (it - 1) & 1);
+        bool waited_pv = false;
+        if (it == 0) {
+          m = bmax;
+        } else if (__any_sync(0xffffffffu, bmax > m + RESCALE_THRESHOLD)) {
+          // rare: raise the reference max of the rows that need it and rescale O in TMEM
+          const float m_new = (bmax > m + RESCALE_THRESHOLD) ? bmax : m;
+          const float alpha = ex2_approx((m - m_new) * LOG2E);
+          mbar_wait(&pv_full[tile], (it - 1) & 1);  // previous PV has landed in O
           tc_fence_after_sync();
+          waited_pv = true;
+          uint32_t ob[32];
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            tmem_ld_32x32b_x32(tmem_pv + c * 32, sreg);
+            tmem_ld_32x32b_x32(tmem_pv + c * 32, ob);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(sreg[i]);
+            for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_pv + c * 32, ob);
           }
+          tmem_st_wait();
+          l *= alpha;
+          m = m_new;
         }
-        if (!__all_sync(0xffffffffu, alpha == 1.0f)) {
-#pragma unroll
-          for (int i = 0; i < HD; ++i) o[i] *= alpha;
-        }
-        l *= alpha;
-        m = m_new;
-        const float mb = m_new * LOG2E;
-        // pass 2: p = exp(s - m), row sum, bf16 P into swizzled smem (A operand of the PV MMA)
+        const float mb = m * LOG2E;
+        // p = exp(s - m) packed to bf16 pairs (in place), row sum in fp32
+        const uint64_t l2e2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
+        uint64_t acc2 = pack2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          tmem_ld_32x32b_x32(tmem_s + c * 32, sreg);
-          tmem_ld_wait();
           const uint32_t bits = mw[c];
-          float pv[32];
+          if (bits == 0xffffffffu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = ex2_approx(fmaf(__uint_as_float(sreg[i]), LOG2E, -mb));
-            if (bits != 0xffffffffu && !((bits >> i) & 1u)) e = 0.f;
-            pv[i] = e;
-            l += e;
+            for (int i = 0; i < 32; i += 2) {
+              float t0, t1;
+              unpack2(ffma2(pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), l2e2, nmb2),
+                      t0, t1);
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+              acc2 = fadd2(acc2, pack2(e0, e1));
+              s[c][i >> 1] = pack_bf16(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(s[c][i]), LOG2E, -mb));
+              float e1 = ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), LOG2E, -mb));
+              if (!((bits >> i) & 1u)) e0 = 0.f;
+              if (!((bits >> (i + 1)) & 1u)) e1 = 0.f;
+              acc2 = fadd2(acc2, pack2(e0, e1));
+              s[c][i >> 1] = pack_bf16(e0, e1);
+            }
           }
+        }
+        float lsum, lsum_hi;
+        unpack2(acc2, lsum, lsum_hi);
+        lsum += lsum_hi;
+        l += lsum;
+        // the P buffer is free once the previous PV MMA (which read it) has completed
+        if (it > 0 && !waited_pv) mbar_wait(&pv_full[tile], (it - 1) & 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
           // columns [c*32, c*32+32) -> sub-tile c/2, 16-byte chunks (c&1)*4 .. +3, XOR row&7
           uint8_t* prow = sPt + (c >> 1) * (BQ * 128) + r * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            u.x = pack_bf16(pv[8 * q + 0], pv[8 * q + 1]);
-            u.y = pack_bf16(pv[8 * q + 2], pv[8 * q + 3]);
-            u.z = pack_bf16(pv[8 * q + 4], pv[8 * q + 5]);
-            u.w = pack_bf16(pv[8 * q + 6], pv[8 * q + 7]);
+            const uint4 u = make_uint4(s[c][4 * q], s[c][4 * q + 1], s[c][4 * q + 2], s[c][4 * q + 3]);
             const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
             *reinterpret_cast<uint4*>(prow + chunk * 16) = u;
           }
         }
         fence_proxy_async_smem();  // st.shared -> visible to the tensor core (async proxy)
-        tc_fence_before_sync();    // order our tcgen05.ld of S / PV before the next MMAs
+        tc_fence_before_sync();    // order our tcgen05.ld/st before the next MMAs
         mbar_arrive(&p_full[tile]);
         ++it;
       }
+      float o[HD];
       if (it > 0) {
         mbar_wait(&pv_full[tile], (it - 1) & 1);
         tc_fence_after_sync();
+        uint32_t ob[32];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          tmem_ld_32x32b_x32(tmem_pv + c * 32, sreg);
+          tmem_ld_32x32b_x32(tmem_pv + c * 32, ob);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(sreg[i]);
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(ob[i]);
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < HD; ++i) o[i] = 0.f;
       }
       const float inv = l > 0.f ? 1.0f / l : 0.f;
       bf16* orow =
@@ -315,7 +370,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     tc_fence_after_sync();
     tmem_dealloc<ATTN_TMEM_COLS>(tmem_base);
   }
