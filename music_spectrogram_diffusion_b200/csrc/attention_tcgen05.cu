@@ -159,30 +159,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P K-major, V MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
+      // descriptor low words (address >> 4 | LBO); stepping = adding (bytes >> 4)
+      const uint32_t q_lo = desc_lo_sw128(smem_u32(sQ));
+      const uint32_t k_lo = desc_lo_sw128(smem_u32(sK));
+      const uint32_t v_lo = desc_lo_sw128(smem_u32(sV));
+      const uint32_t p_lo = desc_lo_sw128(smem_u32(sP));
       // S_t = Q_t K^T : 4 k-steps of 16 along head_dim (32 bytes each inside the swizzle atom)
       auto issue_s = [&](int t, int stage) {
-        const uint32_t k_addr = smem_u32(sK + stage * KV_TILE_BYTES);
+        const uint32_t qa = q_lo + t * (Q_BYTES >> 4);
+        const uint32_t kb = k_lo + stage * (KV_TILE_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(q_addr + t * Q_BYTES + k * 32, 1024, 16);
-          const uint64_t db = make_smem_desc_sw128(k_addr + k * 32, 1024, 16);
-          umma_bf16(tmem_base + t * 128, da, db, idesc_s, k != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_lo(tmem_base + t * 128, qa + k * 2, kb + k * 2, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[t]);
       };
       // PV_t = P_t V : 8 k-steps of 16 keys.  P: sub-tile (k/4) of 16 KB, +32 B per step inside.
       // V (MN-major): 16 keys = 16 rows of 128 B -> +2048 B per step; 8-key groups 1024 B apart.
-      auto issue_pv = [&](int t, int stage, int first_block) {
-        const uint32_t v_addr = smem_u32(sV + stage * KV_TILE_BYTES);
+      auto issue_pv = [&](int t, int stage, uint32_t acc_first) {
+        const uint32_t pa = p_lo + t * (P_BYTES >> 4);
+        const uint32_t vb = v_lo + stage * (KV_TILE_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(
-              p_addr + t * P_BYTES + (k >> 2) * (BQ * 128) + (k & 3) * 32, 1024, 16);
-          const uint64_t db = make_smem_desc_sw128(v_addr + k * 2048, 1024, 16);
-          umma_bf16(tmem_base + 256 + t * 64, da, db, idesc_pv, (k != 0 || !first_block) ? 1u : 0u);
-        }
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_bf16_lo(tmem_base + 256 + t * 64, pa + (k >> 2) * ((BQ * 128) >> 4) + (k & 3) * 2,
+                       vb + k * (2048 >> 4), idesc_pv, k != 0 ? 1u : acc_first);
         umma_commit(&pv_full[t]);
       };
       griddep_wait();  // mask words may come from the previous kernel
@@ -212,7 +211,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int t = 0; t < nq; ++t) {
           mbar_wait(&p_full[t], par);  // P_t published; previous PV_t consumed / rescaled
           tc_fence_after_sync();
-          issue_pv(t, stage, it == 0);
+          issue_pv(t, stage, it == 0 ? 0u : 1u);
         }
         umma_commit(&kv_empty[stage]);  // K/V of this block are dead once the MMAs above retire
         ++it;
@@ -233,6 +232,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       uint8_t* sPt = sP + tile * P_BYTES;
       float m = -INFINITY, l = 0.f;  // reference max (natural units) and running sum
       uint32_t s[4][32];
+      // Ping-pong of the SFU-bound exp phase between the two tiles' warpgroups (named barriers
+      // 2 + tile: "tile may run its exps"): without it both groups run in lockstep and collide on
+      // the SFU while it idles during their max / store / wait phases (ncu: XU 41 % busy).
+      const bool pingpong = (nq == 2);
+      int nact = 0;
+      for (int j = 0; j < nkb; ++j) nact += block_active(mrow, j) ? 1 : 0;
+      if (pingpong && tile == 1 && nact > 0) named_barrier_arrive(2, 256);  // tile 0 goes first
       constexpr float RESCALE_THRESHOLD = 5.545177444f;  // 8 * ln 2: P stays below 2^8
       int it = 0;
       for (int j = 0; j < nkb; ++j) {
@@ -287,22 +293,34 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           m = m_new;
         }
         const float mb = m * LOG2E;
+        if (pingpong) named_barrier_sync(2 + tile, 256);  // my turn on the SFU
         // p = exp(s - m) packed to bf16 pairs (in place), row sum in fp32
         const uint64_t l2e2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
-        uint64_t acc2 = pack2(0.f, 0.f);
+        uint64_t acc2 = pack2(0.f, 0.f), acc2b = pack2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t bits = mw[c];
           if (bits == 0xffffffffu) {
+            // three separate sweeps so that the 32 SFU exps are issued back to back instead of
+            // each pair stalling on its own add/pack (ptxas keeps the source order here)
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               float t0, t1;
               unpack2(ffma2(pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), l2e2, nmb2),
                       t0, t1);
-              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-              acc2 = fadd2(acc2, pack2(e0, e1));
-              s[c][i >> 1] = pack_bf16(e0, e1);
+              s[c][i] = __float_as_uint(t0);
+              s[c][i + 1] = __float_as_uint(t1);
             }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(ex2_approx(__uint_as_float(s[c][i])));
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              acc2 = fadd2(acc2, pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+              acc2b = fadd2(acc2b, pack2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 2)
+              s[c][i >> 1] = pack_bf16(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -315,9 +333,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
           }
         }
-        float lsum, lsum_hi;
+        // hand the SFU to the other tile (the very last hand-over has no taker and is skipped)
+        if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
+        float lsum, lsum_hi, lsum2, lsum2_hi;
         unpack2(acc2, lsum, lsum_hi);
-        lsum += lsum_hi;
+        unpack2(acc2b, lsum2, lsum2_hi);
+        lsum = (lsum + lsum_hi) + (lsum2 + lsum2_hi);
         l += lsum;
         // the P buffer is free once the previous PV MMA (which read it) has completed
         if (it > 0 && !waited_pv) mbar_wait(&pv_full[tile], (it - 1) & 1);

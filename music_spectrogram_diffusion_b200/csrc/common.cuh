@@ -148,6 +148,9 @@ __device__ __forceinline__ void tma_store_wait_read() {  // smem of all but N gr
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void named_barrier_arrive(uint32_t id, uint32_t threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -314,6 +317,44 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+
+// Cheap form for the MMA-issuing thread: the high word of every SWIZZLE_128B descriptor used
+// here is a constant (SBO = 1024 B, version 1, layout type 2) and the low word is
+// (address >> 4) | (LBO 16 B << 16), so stepping through a tile is one 32-bit add per operand
+// instead of rebuilding the 64-bit descriptor (ncu: ~30 uniform-datapath instructions per
+// tcgen05.mma made the small attention MMAs issue-bound).
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) {
+  return ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
 }
 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.

@@ -415,6 +415,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN, 0, 0);
+      const uint32_t a_lo0 = desc_lo_sw128(smem_u32(sA)), b_lo0 = desc_lo_sw128(smem_u32(sB));
       int it = 0, tcount = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
         const int acc = tcount & 1;
@@ -427,14 +428,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_STAGE_BYTES);
+          const uint32_t a_lo = a_lo0 + s * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + s * (Cfg::B_STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 1024, 16);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 1024, 16);
-            umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_2sm_lo(d_tmem, a_lo + k * 2, b_lo + k * 2, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_2sm(&empty_bar[s]);  // frees the slot in BOTH CTAs
         }
         umma_commit_2sm(&tmem_full_bar[acc]);  // accumulator ready in BOTH CTAs
