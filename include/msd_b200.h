@@ -145,6 +145,12 @@ int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t va
 int msd_op_attention(const float* q, const float* k, const float* v, const int32_t* key_mask,
                      int32_t nb, int32_t heads, int32_t Lq, int32_t Lk, float* out, void* stream);
 
+/* Same with a debugging trace: `trace` (device, int64 [2][64][8], may be NULL) receives clock64
+ * stamps of the softmax phases of CTA (0,0,0) for each key block (see attention_tcgen05.cu). */
+int msd_op_attention_trace(const float* q, const float* k, const float* v,
+                           const int32_t* key_mask, int32_t nb, int32_t heads, int32_t Lq,
+                           int32_t Lk, float* out, int64_t* trace, void* stream);
+
 /* LayerNorm (layers.py:632-649) followed by optional FiLM (layers.py:652-666) with explicit
  * scale|bias vector film [2*d] (NULL = none): out f32 (bf16-rounded) [rows, d]. */
 int msd_op_rmsnorm_film(const float* x, const float* gamma, const float* film, int32_t rows,

@@ -43,6 +43,7 @@ struct AttnDev {
   int heads, Lq, Lk;
   const uint32_t* mask_bits;
   int mask_stride_words;
+  long long* trace;  // optional [2 tiles][64 blocks][8] clock64 stamps of CTA (0,0,0), else null
 };
 
 __device__ __forceinline__ bool block_active(const uint32_t* mrow, int blk) {
@@ -248,27 +249,38 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
           mw[0] = w.x; mw[1] = w.y; mw[2] = w.z; mw[3] = w.w;
         }
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 &&
+                        blockIdx.z == 0 && lg == 0 && lane == 0 && it < 64;
+        long long* trp = p.trace + (tile * 64 + it) * 8;
+        if (tr) trp[0] = clock64();
         mbar_wait(&s_full[tile], it & 1);
         tc_fence_after_sync();
+        if (tr) trp[1] = clock64();
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + c * 32, s[c]);
         tmem_ld_wait();
+        if (tr) trp[2] = clock64();
         tc_fence_before_sync();
         mbar_arrive(&s_free[tile]);  // the S buffer may be overwritten by the next block's QK^T
-        // row max over attendable keys (finite: an active block has >= 1 attendable key)
-        float bmax = -INFINITY;
+        // row max over attendable keys (finite: an active block has >= 1 attendable key);
+        // 8 independent partial maxima: a single 128-deep fmax chain cost ~720 cycles per block
+        float mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t bits = mw[c];
           if (bits == 0xffffffffu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, __uint_as_float(s[c][i]));
+            for (int i = 0; i < 32; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[c][i]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if ((bits >> i) & 1u) bmax = fmaxf(bmax, __uint_as_float(s[c][i]));
+              if ((bits >> i) & 1u) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[c][i]));
           }
         }
+        const float bmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                 fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
         bool waited_pv = false;
         if (it == 0) {
           m = bmax;
@@ -293,46 +305,49 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           m = m_new;
         }
         const float mb = m * LOG2E;
+        if (tr) trp[3] = clock64();
         if (pingpong) named_barrier_sync(2 + tile, 256);  // my turn on the SFU
-        // p = exp(s - m) packed to bf16 pairs (in place), row sum in fp32
+        if (tr) trp[4] = clock64();
+        // p = exp(s - m) as bf16 pairs (packed in place into s[c][0..15]), row sum in fp32.
+        // Software-pipelined by one 32-column chunk: the SFU exps of chunk c are independent of
+        // the adds / packs of chunk c-1 issued next to them, so the MUFUs go out back to back.
         const uint64_t l2e2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
         uint64_t acc2 = pack2(0.f, 0.f), acc2b = pack2(0.f, 0.f);
+        float e[2][32];
+        auto exp_chunk = [&](int c, float (&dst)[32]) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t bits = mw[c];
-          if (bits == 0xffffffffu) {
-            // three separate sweeps so that the 32 SFU exps are issued back to back instead of
-            // each pair stalling on its own add/pack (ptxas keeps the source order here)
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float t0, t1;
-              unpack2(ffma2(pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), l2e2, nmb2),
-                      t0, t1);
-              s[c][i] = __float_as_uint(t0);
-              s[c][i + 1] = __float_as_uint(t1);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(ex2_approx(__uint_as_float(s[c][i])));
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              acc2 = fadd2(acc2, pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
-              acc2b = fadd2(acc2b, pack2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 2)
-              s[c][i >> 1] = pack_bf16(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float e0 = ex2_approx(fmaf(__uint_as_float(s[c][i]), LOG2E, -mb));
-              float e1 = ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), LOG2E, -mb));
-              if (!((bits >> i) & 1u)) e0 = 0.f;
-              if (!((bits >> (i + 1)) & 1u)) e1 = 0.f;
-              acc2 = fadd2(acc2, pack2(e0, e1));
-              s[c][i >> 1] = pack_bf16(e0, e1);
-            }
+          for (int i = 0; i < 32; i += 2) {
+            float t0, t1;
+            unpack2(ffma2(pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), l2e2, nmb2),
+                    t0, t1);
+            dst[i] = ex2_approx(t0);
+            dst[i + 1] = ex2_approx(t1);
           }
-        }
+        };
+        auto finish_chunk = [&](int c, float (&src)[32]) {
+          const uint32_t bits = mw[c];
+          if (bits != 0xffffffffu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!((bits >> i) & 1u)) src[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            acc2 = fadd2(acc2, pack2(src[i], src[i + 1]));
+            acc2b = fadd2(acc2b, pack2(src[i + 2], src[i + 3]));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) s[c][i >> 1] = pack_bf16(src[i], src[i + 1]);
+        };
+        exp_chunk(0, e[0]);
+        exp_chunk(1, e[1]);
+        finish_chunk(0, e[0]);
+        exp_chunk(2, e[0]);
+        finish_chunk(1, e[1]);
+        exp_chunk(3, e[1]);
+        finish_chunk(2, e[0]);
+        finish_chunk(3, e[1]);
+        if (tr) trp[5] = clock64();
         // hand the SFU to the other tile (the very last hand-over has no taker and is skipped)
         if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
         float lsum, lsum_hi, lsum2, lsum2_hi;
@@ -342,6 +357,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         l += lsum;
         // the P buffer is free once the previous PV MMA (which read it) has completed
         if (it > 0 && !waited_pv) mbar_wait(&pv_full[tile], (it - 1) & 1);
+        if (tr) trp[6] = clock64();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           // columns [c*32, c*32+32) -> sub-tile c/2, 16-byte chunks (c&1)*4 .. +3, XOR row&7
@@ -356,6 +372,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         fence_proxy_async_smem();  // st.shared -> visible to the tensor core (async proxy)
         tc_fence_before_sync();    // order our tcgen05.ld/st before the next MMAs
         mbar_arrive(&p_full[tile]);
+        if (tr) trp[7] = clock64();
         ++it;
       }
       float o[HD];
@@ -427,6 +444,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   AttnDev d;
   d.O = a.O; d.ldo = a.ldo; d.heads = a.heads; d.Lq = a.Lq; d.Lk = a.Lk;
   d.mask_bits = a.mask_bits; d.mask_stride_words = a.mask_stride_words;
+  d.trace = a.trace;
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch);
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);

@@ -992,6 +992,12 @@ int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t va
 
 int msd_op_attention(const float* q, const float* k, const float* v, const int32_t* key_mask,
                      int32_t nb, int32_t heads, int32_t Lq, int32_t Lk, float* out, void* stream) {
+  return msd_op_attention_trace(q, k, v, key_mask, nb, heads, Lq, Lk, out, nullptr, stream);
+}
+
+int msd_op_attention_trace(const float* q, const float* k, const float* v,
+                           const int32_t* key_mask, int32_t nb, int32_t heads, int32_t Lq,
+                           int32_t Lk, float* out, int64_t* trace, void* stream) {
   MSD_REQUIRE(q && k && v && out, "msd_op_attention: null argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int w = heads * 64;
@@ -1009,7 +1015,14 @@ int msd_op_attention(const float* q, const float* k, const float* v, const int32
     MSD_TRY(tb.get(&bits, static_cast<size_t>(nb) * (Lk / 32)));
     MSD_TRY(launch_mask_bits(key_mask, nb, Lk, bits, st));
   }
-  MSD_TRY(attention(qb, w, kb, w, vb, w, ob, w, nb, heads, Lq, Lk, bits, Lk / 32, st));
+  {
+    AttnArgs aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.Q = qb; aa.ldq = w; aa.K = kb; aa.ldk = w; aa.V = vb; aa.ldv = w; aa.O = ob; aa.ldo = w;
+    aa.nbatch = nb; aa.heads = heads; aa.Lq = Lq; aa.Lk = Lk; aa.mask_bits = bits;
+    aa.mask_stride_words = Lk / 32; aa.trace = reinterpret_cast<long long*>(trace);
+    MSD_TRY(launch_attention(aa, st));
+  }
   MSD_TRY(launch_bf16_to_f32(ob, out, static_cast<long long>(nb) * Lq * w, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;

@@ -119,6 +119,7 @@ struct AttnArgs {
   int nbatch, heads, Lq, Lk;
   const uint32_t* mask_bits; int mask_stride_words;
   const CUtensorMap* tmap_q; const CUtensorMap* tmap_k; const CUtensorMap* tmap_v;
+  long long* trace;  // debugging: per-block clock64 stamps of CTA (0,0,0), see attention kernel
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int attention_configure();
