@@ -262,6 +262,20 @@ class InferenceModel:
   def engine(self) -> engine.Engine:
     return self._get_engine()
 
+  def predict_on_device(self, tokens: torch.Tensor, ctx_features: torch.Tensor,
+                        ctx_mask: torch.Tensor, seed: int = 0,
+                        init_z: Optional[torch.Tensor] = None,
+                        noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device tensors in, device mel out (no host round trip); used by the multi-GPU drivers
+    to hand a segment's prediction to the next segment's context GPU-to-GPU."""
+    eng = self._get_engine()
+    b = tokens.shape[0]
+    if b > self.batch_size:
+      raise ValueError(f'batch of {b} exceeds batch_size={self.batch_size}')
+    eng.encode(tokens.to(torch.int32).contiguous(), ctx_features.to(torch.float32).contiguous(),
+               ctx_mask.to(torch.int32).contiguous())
+    return eng.sample(init_z, noise, seed=seed).clone()
+
   def predict(self, batch: Mapping[str, np.ndarray], seed: int = 0,
               init_z: Optional[np.ndarray] = None, noise: Optional[np.ndarray] = None
               ) -> Tuple[np.ndarray, np.ndarray]:

@@ -128,3 +128,54 @@ def test_sample_internal_rng_is_deterministic(cuda_device, tiny):
   lo, hi = np.log(1e-5) - 1e-3, 4.0 + 1e-3
   assert a.min().item() >= lo and a.max().item() <= hi
   eng.close()
+
+
+def test_inference_model_predict_matches_golden_fixture(cuda_device):
+  """Through the reference-facing API (host numpy batch in, numpy mel out) against the committed
+  fixture tests/golden/tiny_predict.npz (oracle outputs, see make_golden.py)."""
+  import os
+  from music_spectrogram_diffusion_b200 import inference
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'tiny_predict.npz'))
+  t5 = config.t5_tiny()
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = int(g['steps'])
+  diff.classifier_free_guidance.eval_condition_weight = float(g['cond_weight'])
+  lengths = {'inputs': T, 'targets': N, 'targets_context': C}
+  model = inference.InferenceModel.from_config(t5, diff, lengths, 'synthetic:0',
+                                               batch_size=g['tokens'].shape[0])
+  batch = dict(encoder_input_tokens=g['tokens'], encoder_continuous_inputs=g['ctx'],
+               encoder_continuous_mask=g['ctx_mask'],
+               decoder_target_tokens=np.zeros((g['tokens'].shape[0], N, 128), np.float32))
+  mel, scores = model.predict(batch, seed=0, init_z=g['init_z'], noise=g['noise'])
+  assert mel.shape == g['mel'].shape and mel.dtype == np.float32
+  assert scores.shape == (g['tokens'].shape[0],) and not scores.any()
+  span = 4.0 - np.log(1e-5)
+  err = np.abs(mel - g['mel']) / span * 2.0
+  assert err.mean() < 3e-2, (err.mean(), err.max())
+  with pytest.raises(ValueError):
+    model.predict(dict(batch, encoder_input_tokens=g['tokens'][:, :64]))
+
+
+def test_chained_song_single_gpu(cuda_device, tiny):
+  """distributed.synthesize_song on one rank == the colab loop (ipynb:895-935): first segment
+  masked context, later ones fed the previous prediction."""
+  from music_spectrogram_diffusion_b200 import distributed as D, inference
+  t5, params = tiny
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = 6
+  diff.classifier_free_guidance.eval_condition_weight = 2.0
+  lengths = {'inputs': T, 'targets': N, 'targets_context': C}
+  model = inference.InferenceModel.from_config(t5, diff, lengths, 'synthetic:0', 1, params=params)
+  rng = np.random.default_rng(4)
+  segs = [torch.from_numpy(rng.integers(3, 1391, (T,)).astype(np.int32)) for _ in range(3)]
+  song = D.synthesize_song(model.predict_on_device, segs, C, 128, cuda_device, seed=5)
+  assert song.shape == (1, 3 * N, 128) and torch.isfinite(song).all()
+  # manual loop through the host API
+  prev = np.zeros((1, C, 128), np.float32)
+  outs = []
+  for k, s in enumerate(segs):
+    b = dict(encoder_input_tokens=s.numpy()[None], encoder_continuous_inputs=prev,
+             encoder_continuous_mask=np.full((1, C), 0 if k == 0 else 1, np.int32))
+    prev, _ = model.predict(b, seed=5 + k)
+    outs.append(prev)
+  np.testing.assert_allclose(song.cpu().numpy(), np.concatenate(outs, axis=1), atol=1e-5)

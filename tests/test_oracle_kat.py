@@ -1,0 +1,150 @@
+"""CPU: pins the oracle on the reference's own known-answer tests for the hot-path primitives
+(msd/layers_test.py), re-expressed with the same np.random.seed(0) draws, plus the float64
+sampler scalars of SURVEY App. A.4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import msd_oracle as O
+
+
+def _softmax(x, axis=-1):
+  x = x - x.max(axis=axis, keepdims=True)
+  e = np.exp(x)
+  return e / e.sum(axis=axis, keepdims=True)
+
+
+def test_dot_product_attention_kat():
+  """layers_test.py:375-387 (test_dot_product_attention): einsum/softmax, bias, NO scaling."""
+  b, q, h, d, k = 2, 3, 4, 5, 6
+  np.random.seed(0)
+  query = np.random.randn(b, q, h, d)
+  key = np.random.randn(b, k, h, d)
+  value = np.random.randn(b, k, h, d)
+  bias = np.random.randn(b, h, q, k)
+  got = O.dot_product_attention(torch.from_numpy(query), torch.from_numpy(key),
+                                torch.from_numpy(value), torch.from_numpy(bias)).numpy()
+  logits = np.einsum('bqhd,bkhd->bhqk', query, key)
+  weights = _softmax(logits + bias, axis=-1)
+  expected = np.einsum('bhqk,bkhd->bqhd', weights, value)
+  np.testing.assert_allclose(got, expected, atol=1e-6)
+
+
+@pytest.mark.parametrize('f', [20, 22])
+def test_multihead_dot_product_attention_kat(f):
+  """layers_test.py:285-330: kernel layouts [f, h*d] / [h*d, f], no bias, no scale."""
+  b, q, h, d, k = 2, 3, 4, 5, 6
+  np.random.seed(0)
+  inputs_q = np.random.randn(b, q, f)
+  inputs_kv = np.random.randn(b, k, f)
+  query_kernel = np.random.randn(f, h, d)
+  key_kernel = np.random.randn(f, h, d)
+  value_kernel = np.random.randn(f, h, d)
+  out_kernel = np.random.randn(h, d, f)
+  p = {
+      'a/query/kernel': torch.from_numpy(query_kernel.reshape(f, -1)),
+      'a/key/kernel': torch.from_numpy(key_kernel.reshape(f, -1)),
+      'a/value/kernel': torch.from_numpy(value_kernel.reshape(f, -1)),
+      'a/out/kernel': torch.from_numpy(out_kernel.reshape(-1, f)),
+  }
+  y = O.multi_head_dot_product_attention(torch.from_numpy(inputs_q), torch.from_numpy(inputs_kv),
+                                         None, p, 'a', h, d).numpy()
+  query = np.einsum('bqf,fhd->bqhd', inputs_q, query_kernel)
+  key = np.einsum('bkf,fhd->bkhd', inputs_kv, key_kernel)
+  value = np.einsum('bkf,fhd->bkhd', inputs_kv, value_kernel)
+  logits = np.einsum('bqhd,bkhd->bhqk', query, key)
+  weights = _softmax(logits, axis=-1)
+  combined = np.einsum('bhqk,bkhd->bqhd', weights, value)
+  y_expected = np.einsum('bqhd,hdf->bqf', combined, out_kernel)
+  np.testing.assert_allclose(y, y_expected, rtol=1e-5, atol=1e-5)
+
+
+def test_make_attention_mask_multiply_pairwise_fn():
+  """layers_test.py:117-125."""
+  decoder_target_tokens = torch.tensor([[7, 0, 0], [8, 5, 0]])
+  m = (decoder_target_tokens > 0).float()
+  attn_mask = O.make_attention_mask(m, m)
+  expected = np.array([[[[1, 0, 0], [0, 0, 0], [0, 0, 0]]],
+                       [[[1, 1, 0], [1, 1, 0], [0, 0, 0]]]])
+  assert attn_mask.shape == (2, 1, 3, 3)
+  np.testing.assert_array_equal(attn_mask.numpy(), expected)
+
+
+def test_dense_general_kat():
+  """layers_test.py:450-484 (DenseTest): bias-free x @ kernel, incl. joined axes."""
+  np.random.seed(0)
+  x = np.random.randn(2, 3, 4)
+  w = np.random.randn(4, 5)
+  got = O.dense_general(torch.from_numpy(x), torch.from_numpy(w)).numpy()
+  np.testing.assert_allclose(got, x @ w, rtol=1e-12)
+  # two contracted axes == contraction over the flattened axis (how `out` is stored)
+  x2 = np.random.randn(2, 3, 4, 5)
+  w2 = np.random.randn(4, 5, 6)
+  got2 = O.dense_general(torch.from_numpy(x2.reshape(2, 3, 20)),
+                         torch.from_numpy(w2.reshape(20, 6))).numpy()
+  np.testing.assert_allclose(got2, np.einsum('abcd,cde->abe', x2, w2), rtol=1e-10)
+
+
+def test_zero_activations_if_masked():
+  y = torch.ones(2, 3, 4)
+  mask = torch.zeros(2, 1, 3, 5)
+  mask[1, 0, :, 2] = 1
+  out = O.zero_activations_if_masked(y, mask)
+  assert out[0].abs().sum() == 0 and torch.equal(out[1], y[1])
+
+
+# float64 known answers computed from diffusion_utils.py:120-187, 215-222
+A4 = {
+    999: dict(logsnr_t=-20.0, logsnr_s=-12.855470, c_z=0.028092, c_x0=0.001615, sigma=0.999605,
+              x0_scale=22026.4658, eps_scale=1.0),
+    998: dict(logsnr_t=-12.855470, logsnr_s=-11.497462, c_z=0.507120, c_x0=0.002367,
+              sigma=0.861873, x0_scale=618.7718, eps_scale=0.999999),
+    500: dict(logsnr_t=-0.006283, logsnr_s=0.0, c_z=0.995301, c_x0=0.004429, sigma=0.056048,
+              x0_scale=1.4164, eps_scale=0.708217),
+    1: dict(logsnr_t=11.497462, logsnr_s=12.855470, c_z=0.257174, c_x0=0.742826, sigma=0.002747,
+            x0_scale=1.0, eps_scale=0.003187),
+}
+
+
+@pytest.mark.parametrize('i', sorted(A4))
+def test_sampler_scalars_a4(i):
+  c = O.sampler_coefficients(i, 1000, dtype=np.float64)
+  for k, v in A4[i].items():
+    np.testing.assert_allclose(c[k], v, rtol=1e-4, atol=2e-6, err_msg=f'i={i} {k}')
+
+
+def test_cosine_logsnr_constants():
+  b = np.arctan(np.exp(-10.0))
+  a = np.arctan(np.exp(10.0)) - b
+  np.testing.assert_allclose(a, 1.5707055269354342, rtol=1e-14)
+  np.testing.assert_allclose(b, 4.539992973129278e-05, rtol=1e-12)
+  np.testing.assert_allclose(np.log(2e4) / 383, 0.02585766984996378, rtol=1e-14)
+  assert abs(float(O.get_logsnr_t(1.0, dtype=np.float64)) + 20.0) < 1e-9
+  assert abs(float(O.get_logsnr_t(0.0, dtype=np.float64)) - 20.0) < 1e-9
+
+
+def test_timing_signal_shape_and_values():
+  t = torch.tensor([0.001, 0.5, 1.0], dtype=torch.float64)
+  sig = O.get_timing_signal_1d(t * 2e4, 768, max_timescale=2e4)
+  assert sig.shape == (3, 768)
+  inv = np.exp(-np.arange(384) * np.log(2e4) / 383)
+  np.testing.assert_allclose(sig[1, :384].numpy(), np.sin(1e4 * inv), atol=1e-6)
+  np.testing.assert_allclose(sig[1, 384:].numpy(), np.cos(1e4 * inv), atol=1e-6)
+
+
+def test_scale_features_roundtrip():
+  cfg = O.OracleConfig()
+  f = torch.tensor([-20.0, np.log(1e-5), 0.0, 4.0, 9.0])
+  s = O.scale_features(f, cfg, clip=True)
+  np.testing.assert_allclose(s.numpy(), [-1.0, -1.0, (0 - cfg.min_value) / 15.512925 * 2 - 1, 1.0, 1.0],
+                             atol=1e-6)
+  back = O.scale_to_features(s, cfg)
+  np.testing.assert_allclose(back.numpy()[1:4], f.numpy()[1:4], atol=1e-5)
+
+
+def test_get_sequence_length_and_roll():
+  """network.py:28-51."""
+  assert O.get_sequence_length(torch.tensor([1, 1, 0, 0, 0])) == 2
+  assert O.get_sequence_length(torch.tensor([1, 1, 1])) == 3
+  assert O.get_sequence_length(torch.tensor([0, 0, 0])) == 0
+  assert torch.roll(torch.arange(5), 2, 0).tolist() == [3, 4, 0, 1, 2]
