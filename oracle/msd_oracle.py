@@ -500,12 +500,16 @@ def eval_scan(init_z: Tensor, noise: Optional[Tensor], pred_fn: PredFn,
   """diffusion_utils.py:456-476 with the RNG replaced by explicit tensors.
 
   `noise[i]` is the N(0,1) draw the reference takes from fold_in(rng, i) at
-  step i (i = num_steps-1 .. 1; noise[0] is never used).
+  step i (i = num_steps-1 .. 1; noise[0] is never used).  `noise` may also be
+  a callable i -> tensor (lets long runs generate the draws on the fly).
   """
   z = init_z
   for i in range(cfg.num_steps - 1, -1, -1):
-    z = eval_step(z, i, None if noise is None or i == 0 else noise[i],
-                  pred_fn, cfg)
+    if noise is None or i == 0:
+      noise_i = None
+    else:
+      noise_i = noise(i) if callable(noise) else noise[i]
+    z = eval_step(z, i, noise_i, pred_fn, cfg)
     if trajectory is not None:
       trajectory.append(z.clone())
   return z
