@@ -232,15 +232,17 @@ def run_reference(args):
       times.append(sec)
   sec = float(np.mean(times))
   value = lengths['targets'] / sec
-  sample = (f'1 segment: encode + {n_cpu_steps} full CFG diffusion steps of the graph as written, '
-            f'extrapolated linearly to {diff.sampler.schedule.num_steps} steps')
+  sample = (f'oracle port on {cores} threads; 1 of the {args.segments} segments: encode + '
+            f'{n_cpu_steps} full CFG diffusion steps of the graph as written, extrapolated '
+            f'linearly to {diff.sampler.schedule.num_steps} steps (segments are independent, so '
+            'frames/s does not depend on the segment count)')
   line = {
       'impl': 'reference', 'metric': 'mel-frames/sec', 'value': value, 'unit': 'frames/s',
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'x_realtime': value / FRAME_RATE,
-      'config': workload_config(args, t5, lengths, segments=1),
+      'config': workload_config(args, t5, lengths, segments=args.segments),
       'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores,
                        'cores_available': usable_cores(), 'kind': 'port', 'sample': sample},
       'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0,

@@ -179,3 +179,33 @@ def test_chained_song_single_gpu(cuda_device, tiny):
     prev, _ = model.predict(b, seed=5 + k)
     outs.append(prev)
   np.testing.assert_allclose(song.cpu().numpy(), np.concatenate(outs, axis=1), atol=1e-5)
+
+
+@pytest.mark.parametrize('steps', [20, 1000])
+def test_base_with_context_matches_oracle_fixture(cuda_device, steps):
+  """BASELINE config 2: base_with_context, 1 segment, CFG 2.0, fp32 oracle (graph as written) vs
+  the CUDA path, both driven by the library's Philox noise from the same seed.  Fixture:
+  tests/golden/base_predict_<steps>.npz (tests/golden/make_base_golden.py; the 1000-step one costs
+  ~20 CPU-minutes)."""
+  import os
+  import bench
+  from music_spectrogram_diffusion_b200 import inference
+  path = os.path.join(os.path.dirname(__file__), 'golden', f'base_predict_{steps}.npz')
+  if not os.path.exists(path):
+    pytest.skip(f'{os.path.basename(path)} not generated')
+  g = np.load(path)
+  t5 = config.t5_base()
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = int(g['steps'])
+  diff.classifier_free_guidance.eval_condition_weight = float(g['cond_weight'])
+  lengths = dict(config.TASK_FEATURE_LENGTHS_CONTEXT)
+  model = inference.InferenceModel.from_config(t5, diff, lengths,
+                                               f'synthetic:{int(g["weight_seed"])}', batch_size=1)
+  batch = bench.synthetic_batch(1, lengths, seed=int(g['batch_seed']))
+  mel, _ = model.predict(batch, seed=int(g['seed']))
+  span = 4.0 - np.log(1e-5)
+  err = np.abs(mel - g['mel']) / span * 2.0
+  print(f'base {steps} steps: mean|d|={err.mean():.3e} p99={np.quantile(err, 0.99):.3e} '
+        f'max={err.max():.3e}')
+  assert np.isfinite(mel).all()
+  assert err.mean() < 3e-2, (err.mean(), err.max())
