@@ -85,24 +85,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes
+// (or ~10 ms pass) instead of spinning and stealing issue slots from the working warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Bounded: a protocol bug traps (launch failure) after ~10 s instead of hanging the GPU.
 #ifndef MSD_MBAR_SPIN_LIMIT
-#define MSD_MBAR_SPIN_LIMIT (1u << 24)
+#define MSD_MBAR_SPIN_LIMIT 1024u
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > MSD_MBAR_SPIN_LIMIT) __trap();
