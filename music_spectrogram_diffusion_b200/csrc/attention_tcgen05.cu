@@ -44,6 +44,11 @@ struct AttnDev {
   const uint32_t* mask_bits;
   int mask_stride_words;
   long long* trace;  // optional [2 tiles][64 blocks][8] clock64 stamps of CTA (0,0,0), else null
+  // split-KV: blockIdx.z = batch * splits + split; each split covers nkb / splits key blocks and
+  // writes an unnormalised partial (O fp32, reference max m, sum l) that a combine kernel merges.
+  int splits;
+  float* part_o;   // [rows * heads * splits][64]
+  float* part_ml;  // [rows * heads * splits][2]
 };
 
 __device__ __forceinline__ bool block_active(const uint32_t* mrow, int blk) {
@@ -87,6 +92,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
+  const bool ktr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
+                   threadIdx.x == 0;
+  long long* ktrp = p.trace + 2 * 64 * 8;  // CTA-level stamps: entry, setup done, loop end, stores done
+  if (ktr) ktrp[0] = clock64();
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                                   // [2][16 KB]
@@ -105,10 +114,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int qgrp = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qgrp = blockIdx.x, head = blockIdx.y;
+  const int b = blockIdx.z / p.splits, split = blockIdx.z - b * p.splits;
   const int q0 = qgrp * 2 * BQ;                       // first query row of this CTA
   const int nq = (p.Lq - q0 >= 2 * BQ) ? 2 : 1;       // query tiles handled here
-  const int nkb = p.Lk / BKV;
+  const int nkb_all = p.Lk / BKV;
+  const int kb0 = split * nkb_all / p.splits;          // this CTA's key blocks [kb0, nkb)
+  const int nkb = (split + 1) * nkb_all / p.splits;
   const uint32_t* mrow =
       p.mask_bits ? p.mask_bits + static_cast<size_t>(b) * p.mask_stride_words : nullptr;
 
@@ -134,6 +146,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (ktr) ktrp[1] = clock64();
 
   griddep_launch_dependents();
   if (warp >= 8) {
@@ -145,7 +158,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int t = 0; t < nq; ++t)
         tma_load_2d(sQ + t * Q_BYTES, &tmap_q, q_full, head * HD, b * p.Lq + q0 + t * BQ);
       int it = 0;
-      for (int j = 0; j < nkb; ++j) {
+      for (int j = kb0; j < nkb; ++j) {
         if (!block_active(mrow, j)) continue;
         const int s = it % KV_STAGES;
         const uint32_t ph = (it / KV_STAGES) & 1;
@@ -186,7 +199,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         umma_commit(&pv_full[t]);
       };
       griddep_wait();  // mask words may come from the previous kernel
-      int jn = next_active(mrow, 0, nkb);
+      int jn = next_active(mrow, kb0, nkb);
       int it = 0;
       if (jn >= 0) {
         mbar_wait(q_full, 0);
@@ -238,11 +251,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // the SFU while it idles during their max / store / wait phases (ncu: XU 41 % busy).
       const bool pingpong = (nq == 2);
       int nact = 0;
-      for (int j = 0; j < nkb; ++j) nact += block_active(mrow, j) ? 1 : 0;
+      for (int j = kb0; j < nkb; ++j) nact += block_active(mrow, j) ? 1 : 0;
       if (pingpong && tile == 1 && nact > 0) named_barrier_arrive(2, 256);  // tile 0 goes first
       constexpr float RESCALE_THRESHOLD = 5.545177444f;  // 8 * ln 2: P stays below 2^8
       int it = 0;
-      for (int j = 0; j < nkb; ++j) {
+      for (int j = kb0; j < nkb; ++j) {
         if (!block_active(mrow, j)) continue;
         uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         if (mrow != nullptr) {
@@ -375,6 +388,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (tr) trp[7] = clock64();
         ++it;
       }
+      if (ktr) ktrp[2] = clock64();
       float o[HD];
       if (it > 0) {
         mbar_wait(&pv_full[tile], (it - 1) & 1);
@@ -391,10 +405,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
         for (int i = 0; i < HD; ++i) o[i] = 0.f;
       }
+      if (p.splits > 1) {
+        const size_t prow =
+            (static_cast<size_t>(b * p.Lq + q0 + tile * BQ + r) * p.heads + head) * p.splits + split;
+        float4* po = reinterpret_cast<float4*>(p.part_o + prow * HD);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          po[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m, l);
+      } else {
       const float inv = l > 0.f ? 1.0f / l : 0.f;
-      bf16* orow =
-          p.O + static_cast<size_t>(b * p.Lq + q0 + tile * BQ + r) * p.ldo + head * HD;
-      uint4* o4 = reinterpret_cast<uint4*>(orow);
+      // Coalesced store: each warp transposes its 32 rows x 128 B through its own 4 KB slice of
+      // the (now idle) P tile, then writes whole 128-byte row segments (8 lanes per row); the
+      // thread-per-row store cost ~3000 cycles per CTA (32 cache lines per instruction).
+      uint8_t* stg = sPt + lg * 4096;
+      __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         uint4 u;
@@ -402,23 +427,81 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         u.y = pack_bf16(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
         u.z = pack_bf16(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
         u.w = pack_bf16(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
-        o4[q] = u;
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) * 16)) = u;
       }
+      __syncwarp();
+      bf16* obase = p.O + static_cast<size_t>(b * p.Lq + q0 + tile * BQ + lg * 32) * p.ldo + head * HD;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+        const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) * 16));
+        *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.ldo + ch * 8) = u;
+      }
+      }
+      if (ktr) ktrp[3] = clock64();
       tc_fence_before_sync();
     }
   }
   __syncthreads();
+  if (ktr) ktrp[4] = clock64();
   if (warp == 9) {
     tc_fence_after_sync();
     tmem_dealloc<ATTN_TMEM_COLS>(tmem_base);
   }
 }
 
+// Merge the split-KV partials of every (row, head): out = sum_s w_s O_s / sum_s w_s l_s with
+// w_s = exp(m_s - max_s m_s); a split with no attendable key has m = -inf, l = 0 (weight 0).
+__global__ void __launch_bounds__(256)
+attention_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                         bf16* __restrict__ O, int ldo, int heads, int splits, long long n_rh) {
+  griddep_launch_dependents();
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long rh = gid >> 4;  // (row, head) pair; 16 threads x 4 columns each
+  const int c4 = static_cast<int>(gid & 15);
+  if (rh >= n_rh) return;
+  griddep_wait();
+  float mmax = -INFINITY;
+  for (int s = 0; s < splits; ++s) mmax = fmaxf(mmax, part_ml[(rh * splits + s) * 2]);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float lt = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float2 ml = *reinterpret_cast<const float2*>(part_ml + (rh * splits + s) * 2);
+    const float w = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - mmax);
+    const float4 v = *reinterpret_cast<const float4*>(part_o + (rh * splits + s) * HD + c4 * 4);
+    acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    lt += w * ml.y;
+  }
+  const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+  const long long row = rh / heads;
+  const int head = static_cast<int>(rh - row * heads);
+  uint2 u;
+  u.x = pack_bf16(acc.x * inv, acc.y * inv);
+  u.y = pack_bf16(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(O + row * ldo + head * HD + c4 * 4) = u;
+}
+
 }  // namespace
+
+int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
+  const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
+  const int nkb = Lk / BKV;
+  // measured on B200: splitting pays only when fewer than half the SMs would be busy (B = 8
+  // cross-attention, 96 CTAs, is no faster split 3-way: per-CTA fixed costs eat the gain)
+  if (ctas >= 74 || nkb < 6) return 1;
+  int best = 1;
+  for (int s = 2; s <= 8; ++s) {
+    if (nkb % s != 0 || nkb / s < 3) continue;  // >= 3 key blocks per CTA keeps the prologue small
+    if (ctas * s <= 2 * 148) best = s;
+  }
+  return best;
+}
 
 int attention_configure() {
   MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_combine_kernel,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   return 0;
 }
 
@@ -445,12 +528,28 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   d.O = a.O; d.ldo = a.ldo; d.heads = a.heads; d.Lq = a.Lq; d.Lk = a.Lk;
   d.mask_bits = a.mask_bits; d.mask_stride_words = a.mask_stride_words;
   d.trace = a.trace;
-  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch);
+  int splits = (a.part_o != nullptr && a.part_ml != nullptr)
+                   ? (a.splits > 0 ? a.splits : attention_pick_splits(a.nbatch, a.heads, a.Lq, a.Lk))
+                   : 1;
+  if (splits > a.max_splits) splits = a.max_splits > 0 ? a.max_splits : 1;
+  MSD_REQUIRE((a.Lk / BKV) % splits == 0, "attention: %d key blocks not divisible by %d splits",
+              a.Lk / BKV, splits);
+  d.splits = splits; d.part_o = a.part_o; d.part_ml = a.part_ml;
+  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * splits);
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
   MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, stream,
                                tq, tk, tv, d));
   ++g_launch_count;
+  if (splits > 1) {
+    const long long n_rh = static_cast<long long>(a.nbatch) * a.Lq * a.heads;
+    const long long threads = n_rh * 16;
+    MSD_CUDA_CHECK(launch_kernel(attention_combine_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)),
+                                 dim3(256), 0, stream, static_cast<const float*>(a.part_o),
+                                 static_cast<const float*>(a.part_ml), a.O, a.ldo, a.heads, splits,
+                                 n_rh));
+    ++g_launch_count;
+  }
   return 0;
 }
 

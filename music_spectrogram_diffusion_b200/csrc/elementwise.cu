@@ -394,6 +394,21 @@ inline int blocks_for(long long n, int per_block) {
 
 }  // namespace
 
+// Every kernel of the per-step graph asks for the maximum shared-memory carve-out, including the
+// ones that use no shared memory: alternating carve-outs between consecutive kernels forces an SM
+// reconfiguration (the SM must drain first), which also defeats programmatic dependent launch.
+int elementwise_configure() {
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_film_kernel,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(sampler_step_kernel,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(step_advance_kernel,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(init_z_kernel,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  return 0;
+}
+
 int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* out, int ldo,
                    const float* film, const int* step, long long film_step_stride,
                    long long film_offset, int split3, cudaStream_t stream) {

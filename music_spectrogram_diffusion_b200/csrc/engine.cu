@@ -198,6 +198,8 @@ struct msd_ctx {
   bf16* attn = nullptr;    // [R, hh]
   bf16* hmid = nullptr;    // [R, F]
   bf16* qc = nullptr;      // [B*N, hh]
+  float* attn_part_o = nullptr;   // split-KV partials of the cross-attention [B*N*H*8, 64]
+  float* attn_part_ml = nullptr;  // [B*N*H*8, 2]
   float* eps = nullptr;    // [R, nd]
   float* z = nullptr;      // [B*N*nd]
   bf16* z_split = nullptr; // [B*N, 3*nd]
@@ -516,9 +518,11 @@ static int gemm_pos(const bf16* A, int lda, const bf16* B, int ldb, int M, int N
 
 static int attention(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv,
                      bf16* O, int ldo, int nb, int H, int Lq, int Lk, const uint32_t* bits,
-                     int stride_words, cudaStream_t st) {
+                     int stride_words, cudaStream_t st, float* part_o = nullptr,
+                     float* part_ml = nullptr) {
   AttnArgs a;
   memset(&a, 0, sizeof(a));
+  a.part_o = part_o; a.part_ml = part_ml; a.max_splits = 8;
   a.Q = Q; a.ldq = ldq; a.K = K; a.ldk = ldk; a.V = V; a.ldv = ldv; a.O = O; a.ldo = ldo;
   a.nbatch = nb; a.heads = H; a.Lq = Lq; a.Lk = Lk; a.mask_bits = bits;
   a.mask_stride_words = stride_words;
@@ -570,7 +574,7 @@ static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st)
       MSD_TRY(gemm(c->xn, d, w.cross_q, d, Rc, hh, d, EPI_BF16, c->qc, hh, nullptr, st));
       const bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
       MSD_TRY(attention(c->qc, hh, kv, 2 * hh, kv + hh, 2 * hh, c->attn, hh, ncond, c->H, N, c->Mkv,
-                        c->mask_bits, c->Mkv / 32, st));
+                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml));
       MSD_TRY(gemm(c->attn, hh, w.cross_out, hh, Rc, d, hh, EPI_RESID_F32, c->x, d, c->x, st));
     }
     // MLP block (241-256)
@@ -657,6 +661,7 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
               device, prop.major, prop.minor);
   MSD_TRY(gemm_configure());
   MSD_TRY(attention_configure());
+  MSD_TRY(elementwise_configure());
   msd_ctx* c = new msd_ctx();
   c->cfg = *cfg;
   c->device = device;
@@ -683,6 +688,8 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
     if ((rc = A.alloc(&c->attn, R * c->hh))) break;
     if ((rc = A.alloc(&c->hmid, R * c->F))) break;
     if ((rc = A.alloc(&c->qc, BN * c->hh))) break;
+    if ((rc = A.alloc(&c->attn_part_o, BN * c->H * 8 * 64))) break;
+    if ((rc = A.alloc(&c->attn_part_ml, BN * c->H * 8 * 2))) break;
     if ((rc = A.alloc(&c->eps, R * c->nd))) break;
     if ((rc = A.alloc(&c->z, BN * c->nd))) break;
     if ((rc = A.alloc(&c->z_split, BN * 3 * c->nd))) break;
@@ -1021,6 +1028,14 @@ int msd_op_attention_trace(const float* q, const float* k, const float* v,
     aa.Q = qb; aa.ldq = w; aa.K = kb; aa.ldk = w; aa.V = vb; aa.ldv = w; aa.O = ob; aa.ldo = w;
     aa.nbatch = nb; aa.heads = heads; aa.Lq = Lq; aa.Lk = Lk; aa.mask_bits = bits;
     aa.mask_stride_words = Lk / 32; aa.trace = reinterpret_cast<long long*>(trace);
+    float *po = nullptr, *pml = nullptr;
+    MSD_TRY(tb.get(&po, static_cast<size_t>(nb) * Lq * heads * 8 * 64));
+    MSD_TRY(tb.get(&pml, static_cast<size_t>(nb) * Lq * heads * 8 * 2));
+    aa.part_o = po; aa.part_ml = pml; aa.max_splits = 8;
+    {
+      const char* f = getenv("MSD_ATTN_SPLITS");  // test hook: force a split count
+      aa.splits = f ? atoi(f) : 0;
+    }
     MSD_TRY(launch_attention(aa, st));
   }
   MSD_TRY(launch_bf16_to_f32(ob, out, static_cast<long long>(nb) * Lq * w, st));

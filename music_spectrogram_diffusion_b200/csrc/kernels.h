@@ -120,7 +120,11 @@ struct AttnArgs {
   const uint32_t* mask_bits; int mask_stride_words;
   const CUtensorMap* tmap_q; const CUtensorMap* tmap_k; const CUtensorMap* tmap_v;
   long long* trace;  // debugging: per-block clock64 stamps of CTA (0,0,0), see attention kernel
+  // split-KV workspace (optional): part_o [rows*heads*max_splits*64] f32, part_ml [..*2] f32;
+  // splits 0 = choose automatically (attention_pick_splits), capped by max_splits.
+  float* part_o; float* part_ml; int splits; int max_splits;
 };
+int attention_pick_splits(int nbatch, int heads, int Lq, int Lk);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int attention_configure();
 
@@ -129,6 +133,7 @@ int attention_configure();
 // ---------------------------------------------------------------------------
 // y = rmsnorm(x; g) [ * (1 + s) + b ], written as bf16.  s|b = film[(*step) * film_stride +
 // film_offset + {0, d}] when film != nullptr.  split3: write [hi | lo | hi] (3*d wide).
+int elementwise_configure();
 int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* out, int ldo,
                    const float* film, const int* step, long long film_step_stride,
                    long long film_offset, int split3, cudaStream_t stream);

@@ -28,11 +28,17 @@ def test_dense_general(cuda_device, M, N, K, variant, block_n):
   assert err < 2e-4 * np.sqrt(K), f'max err {err}'
 
 
+@pytest.mark.parametrize('splits', [0, 1, 3])
 @pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
     (1, 1, 128, 128, False), (2, 2, 128, 256, False), (2, 3, 256, 384, True),
-    (1, 2, 256, 2304, True), (3, 2, 128, 128, True)])
-def test_dot_product_attention(cuda_device, nb, heads, Lq, Lk, masked):
+    (1, 2, 256, 2304, True), (3, 2, 128, 128, True), (2, 2, 256, 768, True)])
+def test_dot_product_attention(cuda_device, monkeypatch, nb, heads, Lq, Lk, masked, splits):
+  """splits: 0 = automatic split-KV choice, 1 = single pass, 3 = forced 3-way split + combine."""
   from music_spectrogram_diffusion_b200 import engine
+  if splits == 3 and (Lk // 128) % 3:
+    pytest.skip('key blocks not divisible by 3')
+  if splits:
+    monkeypatch.setenv('MSD_ATTN_SPLITS', str(splits))
   g = torch.Generator().manual_seed(nb * 1000 + Lk)
   w = heads * 64
   q = bf16_round(torch.randn(nb, Lq, w, generator=g) * 0.5)
