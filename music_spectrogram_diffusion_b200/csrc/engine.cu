@@ -48,6 +48,7 @@ struct ProfRecorder {
   std::vector<Rec> recs;
 };
 ProfRecorder* g_prof = nullptr;
+bool g_pdl_skip_next = false;
 bool g_use_pdl = [] {
   const char* v = getenv("MSD_PDL");
   return !(v && v[0] == '0');
@@ -175,8 +176,9 @@ struct msd_ctx {
   int d = 0, H = 0, hh = 0, F = 0, T = 0, N = 0, C = 0, Mkv = 0, nd = 0, Bmax = 0, passes = 2;
   bool weights_loaded = false;
   Arena arena;
-  cudaStream_t work = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t work = nullptr, work2 = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  bool two_streams = false;
 
   // ---- parameters
   float* tok_emb = nullptr;  // [vocab, d] f32
@@ -549,16 +551,13 @@ static int run_encoder(msd_ctx* c, const Encoder& e, int B, int len, const uint3
   return 0;
 }
 
-// Decoder.__call__ (network.py:360-457) over `total` segments of which the first `ncond`
-// cross-attend to the cached encodings.  Input: c->z_split; output: c->eps [total*N, nd].
-static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st) {
-  const int d = c->d, hh = c->hh, F = c->F, N = c->N, nd = c->nd;
+// Single-chain variant: conditional + unconditional rows batched in every kernel except the
+// cross-attention block (used by the profiler and when MSD_TWO_STREAMS=0).
+static int decoder_layers_batched(msd_ctx* c, int ncond, int total, cudaStream_t st) {
+  const int d = c->d, hh = c->hh, F = c->F, N = c->N;
   const int R = total * N, Rc = ncond * N;
   const int Ld = c->cfg.num_decoder_layers;
   const long long fstride = static_cast<long long>(2) * Ld * 2 * d;
-  // continuous_inputs_projection + position encodings (420-427); both passes start equal.
-  MSD_TRY(gemm_pos(c->z_split, 3 * nd, c->dec_in_proj, 3 * nd, B * N, d, 3 * nd, c->x, c->dec_pos,
-                   N, nullptr, total > B ? B * N : 0, st));
   for (int l = 0; l < Ld; ++l) {
     const DecLayer& w = c->dec[l];
     // self-attention block (174-193)
@@ -582,6 +581,79 @@ static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st)
                            static_cast<long long>(2 * l + 1) * 2 * d, 0, st));
     MSD_TRY(gemm(c->xn, d, w.mlp.wi, d, R, 2 * F, d, EPI_GATED_GELU, c->hmid, F, nullptr, st));
     MSD_TRY(gemm(c->hmid, F, w.mlp.wo, F, R, d, F, EPI_RESID_F32, c->x, d, c->x, st));
+  }
+  return 0;
+}
+
+
+// The 12 DecoderLayers (network.py:161-258) over segments [seg0, seg0 + nseg) of the row buffers;
+// `cross` = these rows cross-attend to the cached encodings (conditional pass).
+static int decoder_layers(msd_ctx* c, int seg0, int nseg, bool cross, cudaStream_t st) {
+  const int d = c->d, hh = c->hh, F = c->F, N = c->N;
+  const int R = nseg * N;
+  const size_t r0 = static_cast<size_t>(seg0) * N;
+  const int Ld = c->cfg.num_decoder_layers;
+  const long long fstride = static_cast<long long>(2) * Ld * 2 * d;
+  float* x = c->x + r0 * d;
+  bf16* xn = c->xn + r0 * d;  // [rows, d] view of the scratch buffer (disjoint per range)
+  bf16* qkv = c->qkv + r0 * 3 * hh;
+  bf16* attn = c->attn + r0 * hh;
+  bf16* hmid = c->hmid + r0 * F;
+  for (int l = 0; l < Ld; ++l) {
+    const DecLayer& w = c->dec[l];
+    // self-attention block (174-193)
+    MSD_TRY(launch_rmsnorm(x, w.ln_self, R, d, xn, d, c->film, c->d_step, fstride,
+                           static_cast<long long>(2 * l) * 2 * d, 0, st));
+    MSD_TRY(gemm(xn, d, w.self_attn.qkv, d, R, 3 * hh, d, EPI_BF16, qkv, 3 * hh, nullptr, st));
+    MSD_TRY(attention(qkv, 3 * hh, qkv + hh, 3 * hh, qkv + 2 * hh, 3 * hh, attn, hh, nseg, c->H, N,
+                      N, nullptr, 0, st));
+    MSD_TRY(gemm(attn, hh, w.self_attn.out, hh, R, d, hh, EPI_RESID_F32, x, d, x, st));
+    // cross-attention block (196-235), conditioned rows only (they are segments [0, ncond))
+    if (cross) {
+      MSD_TRY(launch_rmsnorm(x, w.ln_cross, R, d, xn, d, nullptr, nullptr, 0, 0, 0, st));
+      MSD_TRY(gemm(xn, d, w.cross_q, d, R, hh, d, EPI_BF16, c->qc, hh, nullptr, st));
+      const bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
+      MSD_TRY(attention(c->qc, hh, kv, 2 * hh, kv + hh, 2 * hh, attn, hh, nseg, c->H, N, c->Mkv,
+                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml));
+      MSD_TRY(gemm(attn, hh, w.cross_out, hh, R, d, hh, EPI_RESID_F32, x, d, x, st));
+    }
+    // MLP block (241-256)
+    MSD_TRY(launch_rmsnorm(x, w.ln_mlp, R, d, xn, d, c->film, c->d_step, fstride,
+                           static_cast<long long>(2 * l + 1) * 2 * d, 0, st));
+    MSD_TRY(gemm(xn, d, w.mlp.wi, d, R, 2 * F, d, EPI_GATED_GELU, hmid, F, nullptr, st));
+    MSD_TRY(gemm(hmid, F, w.mlp.wo, F, R, d, F, EPI_RESID_F32, x, d, x, st));
+  }
+  return 0;
+}
+
+// Decoder.__call__ (network.py:360-457) over `total` segments of which the first `ncond`
+// cross-attend to the cached encodings.  Input: c->z_split; output: c->eps [total*N, nd].
+// With `two_streams` the conditional and unconditional passes -- independent until the guidance
+// combine -- run as two concurrent kernel chains (fork/join on c->work2), so one chain's
+// low-parallelism kernels (cross-attention: 96 CTAs; N=768 GEMMs: 32-64 tiles) and per-kernel
+// prologue/tail bubbles are filled by the other chain's kernels.
+static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st,
+                       bool two_streams = false) {
+  const int d = c->d, N = c->N, nd = c->nd;
+  const int R = total * N;
+  // continuous_inputs_projection + position encodings (420-427); both passes start equal.
+  MSD_TRY(gemm_pos(c->z_split, 3 * nd, c->dec_in_proj, 3 * nd, B * N, d, 3 * nd, c->x, c->dec_pos,
+                   N, nullptr, total > B ? B * N : 0, st));
+  const int nuncond = total - ncond;
+  if (two_streams && ncond > 0 && nuncond > 0) {
+    MSD_CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
+    MSD_CUDA_CHECK(cudaStreamWaitEvent(c->work2, c->ev_fork, 0));
+    g_pdl_skip_next = true;  // first kernel of the side chain depends on another stream
+    MSD_TRY(decoder_layers(c, ncond, nuncond, false, c->work2));
+    MSD_TRY(decoder_layers(c, 0, ncond, true, st));
+    MSD_CUDA_CHECK(cudaEventRecord(c->ev_join, c->work2));
+    MSD_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    g_pdl_skip_next = true;  // the join kernel has two predecessors
+  } else if (ncond > 0 && nuncond > 0) {
+    // one chain, both passes batched per kernel except the cross-attention block
+    MSD_TRY(decoder_layers_batched(c, ncond, total, st));
+  } else {
+    MSD_TRY(decoder_layers(c, 0, total, ncond > 0, st));
   }
   // decoder_norm + spec_out_dense in split precision (445-456: fp32 "for stability")
   MSD_TRY(launch_rmsnorm(c->x, c->dec_norm, R, d, c->xn, 3 * d, nullptr, nullptr, 0, 0, 1, st));
@@ -675,7 +747,18 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
   const size_t ER = static_cast<size_t>(c->Bmax) * (c->T > c->C ? c->T : c->C);
   int rc = 0;
   do {
+    {
+      // Opt-in experiment (MSD_TWO_STREAMS=1): conditional / unconditional passes as two concurrent
+      // kernel chains.  Measured on B200 at B = 8: 1080 vs 1123 frames/s for the single chain
+      // (every GEMM / attention CTA owns a whole SM's shared memory, so the chains mostly
+      // time-share SMs, and the half-height GEMMs are less efficient) -> off by default.
+      const char* ts = getenv("MSD_TWO_STREAMS");
+      c->two_streams = (ts && ts[0] == '1');
+    }
     if (cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->work2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
       set_error("msd_create: stream/event creation failed");
@@ -729,6 +812,9 @@ void msd_destroy(msd_ctx* c) {
   c->arena.release();
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->work2) cudaStreamDestroy(c->work2);
   if (c->work) cudaStreamDestroy(c->work);
   delete c;
 }
@@ -867,7 +953,7 @@ int msd_sample(msd_ctx* c, const float* init_z, const float* noise, uint64_t see
     const unsigned long long before = g_launch_count;
     cudaGraph_t graph = nullptr;
     MSD_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = run_decoder(c, B, B, c->passes * B, st);
+    int rc = run_decoder(c, B, B, c->passes * B, st, c->two_streams);
     if (rc == 0) rc = sampler_step(c, B, noise, seed, mel_out, st);
     if (rc == 0) rc = launch_step_advance(c->d_step, st);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);

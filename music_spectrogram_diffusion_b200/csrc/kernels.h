@@ -40,6 +40,7 @@ struct ProfScope {
 // PDL is enabled (default; MSD_PDL=0 disables).  Works under stream capture (programmatic edges).
 // ---------------------------------------------------------------------------
 extern bool g_use_pdl;
+extern bool g_pdl_skip_next;  // next launch has a cross-stream dependency: plain launch
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                  cudaStream_t stream, Args&&... args) {
@@ -52,7 +53,8 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = (g_use_pdl && !g_pdl_skip_next) ? 1 : 0;
+  g_pdl_skip_next = false;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
