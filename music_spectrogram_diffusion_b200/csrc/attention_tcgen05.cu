@@ -18,6 +18,8 @@
 //                       rescaled in TMEM with tcgen05.ld/st), exact because the final division
 //                       uses the same reference max for numerator and denominator
 // Key blocks whose 128 mask bits are all zero are skipped by every role.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -49,16 +51,45 @@ struct AttnDev {
   int splits;
   float* part_o;   // [rows * heads * splits][64]
   float* part_ml;  // [rows * heads * splits][2]
+  // tail mode (splits == 1, tail > 0): blockIdx.z = role * nbatch + batch.  Role 1 ("short") CTAs
+  // cover the last `tail` key blocks and publish an unnormalised partial per softmax warp; role 0
+  // ("long") CTAs cover the rest, are scheduled first (lower block index), and merge the partial of
+  // their short partner before the final store.  Balances grids that fill 50-100 % of the SMs.
+  int tail, nbatch;
+  int kv_static;    // K, V and mask_bits are not produced by the preceding kernels (see TMA warp)
+  uint32_t* flags;  // [nbatch * heads * q-tiles * 4] one per softmax warp, 0 outside a launch
 };
 
-__device__ __forceinline__ bool block_active(const uint32_t* mrow, int blk) {
-  if (mrow == nullptr) return true;
-  const uint4 w = *reinterpret_cast<const uint4*>(mrow + blk * 4);
-  return (w.x | w.y | w.z | w.w) != 0u;
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __forceinline__ int next_active(const uint32_t* mrow, int from, int nkb) {
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Bit j = key block j has at least one attendable key.  One coalesced pass by a whole warp
+// (a serial loop of dependent global loads cost ~3000 cycles per CTA for 18 blocks).
+__device__ __forceinline__ uint64_t active_blocks(const uint32_t* mrow, int nkb_all, int lane) {
+  if (mrow == nullptr) return ~0ull;
+  uint32_t word[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = h * 32 + lane;
+    bool a = false;
+    if (j < nkb_all) {
+      const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
+      a = (w.x | w.y | w.z | w.w) != 0u;
+    }
+    word[h] = __ballot_sync(0xffffffffu, a);
+  }
+  return static_cast<uint64_t>(word[0]) | (static_cast<uint64_t>(word[1]) << 32);
+}
+__device__ __forceinline__ bool block_active(uint64_t act, int blk) { return (act >> blk) & 1ull; }
+__device__ __forceinline__ int next_active(uint64_t act, int from, int nkb) {
   for (int j = from; j < nkb; ++j)
-    if (block_active(mrow, j)) return j;
+    if (block_active(act, j)) return j;
   return -1;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -85,6 +116,12 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
@@ -115,12 +152,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int qgrp = blockIdx.x, head = blockIdx.y;
-  const int b = blockIdx.z / p.splits, split = blockIdx.z - b * p.splits;
+  const int role = p.tail > 0 ? static_cast<int>(blockIdx.z) / p.nbatch : 0;
+  const int b = p.tail > 0 ? static_cast<int>(blockIdx.z) - role * p.nbatch
+                           : static_cast<int>(blockIdx.z) / p.splits;
+  const int split = p.tail > 0 ? 0 : static_cast<int>(blockIdx.z) - b * p.splits;
   const int q0 = qgrp * 2 * BQ;                       // first query row of this CTA
   const int nq = (p.Lq - q0 >= 2 * BQ) ? 2 : 1;       // query tiles handled here
   const int nkb_all = p.Lk / BKV;
-  const int kb0 = split * nkb_all / p.splits;          // this CTA's key blocks [kb0, nkb)
-  const int nkb = (split + 1) * nkb_all / p.splits;
+  // this CTA's key blocks [kb0, nkb)
+  const int kb0 = p.tail > 0 ? (role ? nkb_all - p.tail : 0) : split * nkb_all / p.splits;
+  const int nkb = p.tail > 0 ? (role ? nkb_all : nkb_all - p.tail) : (split + 1) * nkb_all / p.splits;
   const uint32_t* mrow =
       p.mask_bits ? p.mask_bits + static_cast<size_t>(b) * p.mask_stride_words : nullptr;
 
@@ -152,24 +193,36 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp >= 8) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 8) {
+    // kv_static: K, V and the key mask were written long before the preceding kernel (the
+    // cross-attention cache of a diffusion step), so the first ring-full of K/V tiles is
+    // requested ahead of the dependency wait; only Q comes from the preceding kernel.
+    if (!p.kv_static) griddep_wait();
+    const uint64_t act = active_blocks(mrow, nkb_all, lane);
     if (lane == 0) {
-      griddep_wait();
-      mbar_arrive_expect_tx(q_full, nq * Q_BYTES);
-      for (int t = 0; t < nq; ++t)
-        tma_load_2d(sQ + t * Q_BYTES, &tmap_q, q_full, head * HD, b * p.Lq + q0 + t * BQ);
-      int it = 0;
-      for (int j = kb0; j < nkb; ++j) {
-        if (!block_active(mrow, j)) continue;
+      int it = 0, j = kb0;
+      auto load_kv = [&](int jb) {
         const int s = it % KV_STAGES;
         const uint32_t ph = (it / KV_STAGES) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&kv_full[s], 2 * KV_TILE_BYTES);
-        tma_load_2d(sK + s * KV_TILE_BYTES, &tmap_k, &kv_full[s], head * HD, b * p.Lk + j * BKV);
-        tma_load_2d(sV + s * KV_TILE_BYTES, &tmap_v, &kv_full[s], head * HD, b * p.Lk + j * BKV);
+        tma_load_2d(sK + s * KV_TILE_BYTES, &tmap_k, &kv_full[s], head * HD, b * p.Lk + jb * BKV);
+        tma_load_2d(sV + s * KV_TILE_BYTES, &tmap_v, &kv_full[s], head * HD, b * p.Lk + jb * BKV);
         ++it;
+      };
+      if (p.kv_static) {
+        for (; j < nkb && it < KV_STAGES; ++j)
+          if (block_active(act, j)) load_kv(j);
+        griddep_wait();
       }
+      mbar_arrive_expect_tx(q_full, nq * Q_BYTES);
+      for (int t = 0; t < nq; ++t)
+        tma_load_2d(sQ + t * Q_BYTES, &tmap_q, q_full, head * HD, b * p.Lq + q0 + t * BQ);
+      for (; j < nkb; ++j)
+        if (block_active(act, j)) load_kv(j);
     }
   } else if (warp == 9) {
+    if (!p.kv_static) griddep_wait();  // mask words may come from the previous kernel
+    const uint64_t act = active_blocks(mrow, nkb_all, lane);
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P K-major, V MN-major
@@ -198,8 +251,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                        vb + k * (2048 >> 4), idesc_pv, k != 0 ? 1u : acc_first);
         umma_commit(&pv_full[t]);
       };
-      griddep_wait();  // mask words may come from the previous kernel
-      int jn = next_active(mrow, kb0, nkb);
+      int jn = next_active(act, kb0, nkb);
       int it = 0;
       if (jn >= 0) {
         mbar_wait(q_full, 0);
@@ -208,7 +260,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int t = 0; t < nq; ++t) issue_s(t, 0);
       }
       while (jn >= 0) {
-        jn = next_active(mrow, jn + 1, nkb);
+        jn = next_active(act, jn + 1, nkb);
         const int stage = it % KV_STAGES;
         const int nstage = (it + 1) % KV_STAGES;
         const uint32_t par = it & 1;
@@ -236,7 +288,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ------------------------- softmax / output warp groups -------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int tile = warp >> 2;  // 0: warps 0..3, 1: warps 4..7
-    griddep_wait();  // mask words are read and O is written by these warps
+    if (!p.kv_static) griddep_wait();  // mask words may come from the previous kernel
+    const uint64_t act = active_blocks(mrow, nkb_all, lane);
+    griddep_wait();  // O is written by these warps
     if (tile < nq) {
       const int lg = warp & 3;
       const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
@@ -249,14 +303,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // Ping-pong of the SFU-bound exp phase between the two tiles' warpgroups (named barriers
       // 2 + tile: "tile may run its exps"): without it both groups run in lockstep and collide on
       // the SFU while it idles during their max / store / wait phases (ncu: XU 41 % busy).
-      const bool pingpong = (nq == 2);
       int nact = 0;
-      for (int j = kb0; j < nkb; ++j) nact += block_active(mrow, j) ? 1 : 0;
+      for (int j = kb0; j < nkb; ++j) nact += block_active(act, j) ? 1 : 0;
+      const bool pingpong = (nq == 2);
       if (pingpong && tile == 1 && nact > 0) named_barrier_arrive(2, 256);  // tile 0 goes first
       constexpr float RESCALE_THRESHOLD = 5.545177444f;  // 8 * ln 2: P stays below 2^8
       int it = 0;
       for (int j = kb0; j < nkb; ++j) {
-        if (!block_active(mrow, j)) continue;
+        if (!block_active(act, j)) continue;
         uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         if (mrow != nullptr) {
           const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
@@ -285,7 +339,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint32_t bits = mw[c];
           if (bits == 0xffffffffu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[c][i]));
+            for (int i = 0; i < 32; i += 2)
+              mx[(i >> 1) & 7] = fmax3(mx[(i >> 1) & 7], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -326,40 +381,50 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // the adds / packs of chunk c-1 issued next to them, so the MUFUs go out back to back.
         const uint64_t l2e2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
         uint64_t acc2 = pack2(0.f, 0.f), acc2b = pack2(0.f, 0.f);
-        float e[2][32];
-        auto exp_chunk = [&](int c, float (&dst)[32]) {
+        // Two copies of the phase behind a warp-uniform branch: with every key of the block
+        // attendable (the common case) no select instructions are issued.  The phase is bound by
+        // the issue rate of the single warp per sub-partition that runs it (ping-pong), i.e. by
+        // its instruction count (measured ~2.5 cycles per instruction), not by the SFU.
+        auto exp_phase = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
+          float e[2][32];
+          auto exp_chunk = [&](int c, float (&dst)[32]) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float t0, t1;
-            unpack2(ffma2(pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), l2e2, nmb2),
-                    t0, t1);
-            dst[i] = ex2_approx(t0);
-            dst[i + 1] = ex2_approx(t1);
-          }
+            for (int i = 0; i < 32; i += 2) {
+              const uint64_t t2 =
+                  ffma2(pack2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), l2e2, nmb2);
+              float t0, t1;
+              unpack2(t2, t0, t1);
+              dst[i] = ex2_approx(t0);
+              dst[i + 1] = ex2_approx(t1);
+            }
+          };
+          auto finish_chunk = [&](int c, float (&src)[32]) {
+            if (MASKED) {
+              const uint32_t bits = mw[c];
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (!((bits >> i) & 1u)) src[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              acc2 = fadd2(acc2, pack2(src[i], src[i + 1]));
+              acc2b = fadd2(acc2b, pack2(src[i + 2], src[i + 3]));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) s[c][i >> 1] = pack_bf16(src[i], src[i + 1]);
+          };
+          exp_chunk(0, e[0]);
+          exp_chunk(1, e[1]);
+          finish_chunk(0, e[0]);
+          exp_chunk(2, e[0]);
+          finish_chunk(1, e[1]);
+          exp_chunk(3, e[1]);
+          finish_chunk(2, e[0]);
+          finish_chunk(3, e[1]);
         };
-        auto finish_chunk = [&](int c, float (&src)[32]) {
-          const uint32_t bits = mw[c];
-          if (bits != 0xffffffffu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (!((bits >> i) & 1u)) src[i] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            acc2 = fadd2(acc2, pack2(src[i], src[i + 1]));
-            acc2b = fadd2(acc2b, pack2(src[i + 2], src[i + 3]));
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) s[c][i >> 1] = pack_bf16(src[i], src[i + 1]);
-        };
-        exp_chunk(0, e[0]);
-        exp_chunk(1, e[1]);
-        finish_chunk(0, e[0]);
-        exp_chunk(2, e[0]);
-        finish_chunk(1, e[1]);
-        exp_chunk(3, e[1]);
-        finish_chunk(2, e[0]);
-        finish_chunk(3, e[1]);
+        if ((mw[0] & mw[1] & mw[2] & mw[3]) == 0xffffffffu) exp_phase(std::false_type{});
+        else exp_phase(std::true_type{});
         if (tr) trp[5] = clock64();
         // hand the SFU to the other tile (the very last hand-over has no taker and is skipped)
         if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
@@ -405,7 +470,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
         for (int i = 0; i < HD; ++i) o[i] = 0.f;
       }
-      if (p.splits > 1) {
+      // tail mode: one partial slot per softmax warp, laid out [16 float4][32 lanes] so that both
+      // the short CTA's stores and the long CTA's loads are 512-byte coalesced
+      const size_t wslot =
+          ((static_cast<size_t>(b) * p.heads + head) * ((p.Lq + BQ - 1) / BQ) + qgrp * 2 + tile) * 4 + lg;
+      if (p.tail > 0 && role == 1) {
+        float4* po = reinterpret_cast<float4*>(p.part_o + wslot * (32 * HD));
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          po[q * 32 + lane] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        reinterpret_cast<float2*>(p.part_ml + wslot * 64)[lane] = make_float2(m, l);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(p.flags + wslot, 1u);
+      } else if (p.splits > 1) {
         const size_t prow =
             (static_cast<size_t>(b * p.Lq + q0 + tile * BQ + r) * p.heads + head) * p.splits + split;
         float4* po = reinterpret_cast<float4*>(p.part_o + prow * HD);
@@ -414,6 +492,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           po[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m, l);
       } else {
+      if (p.tail > 0) {
+        // merge the short partner's partial: O = w_l O_l + w_s O_s, l likewise, w = exp(m - max m)
+        for (uint32_t spins = 0; ld_acquire_gpu(p.flags + wslot) == 0u; ++spins) {
+          __nanosleep(100);
+          if (spins > (1u << 24)) __trap();  // partner never published: fail loudly, do not hang
+        }
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + wslot * 64) + lane);
+        const float mm = fmaxf(m, ml.x);
+        const float wl = (m == -INFINITY) ? 0.f : ex2_approx((m - mm) * LOG2E);
+        const float ws = (ml.x == -INFINITY) ? 0.f : ex2_approx((ml.x - mm) * LOG2E);
+        const float4* po = reinterpret_cast<const float4*>(p.part_o + wslot * (32 * HD));
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 v = __ldcg(po + q * 32 + lane);
+          o[4 * q + 0] = o[4 * q + 0] * wl + v.x * ws;
+          o[4 * q + 1] = o[4 * q + 1] * wl + v.y * ws;
+          o[4 * q + 2] = o[4 * q + 2] * wl + v.z * ws;
+          o[4 * q + 3] = o[4 * q + 3] * wl + v.w * ws;
+        }
+        l = l * wl + ml.y * ws;
+        __syncwarp();
+        if (lane == 0) p.flags[wslot] = 0u;  // re-armed for the next launch (stream ordered)
+      }
       const float inv = l > 0.f ? 1.0f / l : 0.f;
       // Coalesced store: each warp transposes its 32 rows x 128 B through its own 4 KB slice of
       // the (now idle) P tile, then writes whole 128-byte row segments (8 lanes per row); the
@@ -497,6 +598,27 @@ int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
   return best;
 }
 
+// Tail split for grids that fill between half and all of the SMs (one CTA per SM): long CTAs take
+// nkb - t key blocks, short CTAs t, shorts run in the SMs the longs leave free (several rounds).
+// Cost model in key-block units with a fixed per-CTA cost F (setup + epilogue, measured ~4.5 on B200: 18 blocks / 96 CTAs -> tail 4).
+int attention_pick_tail(int nbatch, int heads, int Lq, int Lk) {
+  const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
+  const int nkb = Lk / BKV;
+  const int sms = 148;
+  if (ctas < sms / 2 || ctas >= sms || nkb < 6) return 0;
+  const int free_sms = sms - ctas;
+  const int rounds = (ctas + free_sms - 1) / free_sms;
+  const float F = 4.5f;
+  int best = 0;
+  float best_t = (nkb + F) * 0.92f;  // must beat the unsplit kernel by a margin
+  for (int t = 1; t <= nkb / 2; ++t) {
+    const float tl = (nkb - t) + F + 0.3f, ts = rounds * (t + F);
+    const float tt = tl > ts ? tl : ts;
+    if (tt < best_t) { best_t = tt; best = t; }
+  }
+  return best;
+}
+
 int attention_configure() {
   MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
@@ -508,6 +630,7 @@ int attention_configure() {
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   MSD_REQUIRE(a.Lq % BQ == 0 && a.Lk % BKV == 0,
               "attention: Lq=%d and Lk=%d must be multiples of 128", a.Lq, a.Lk);
+  MSD_REQUIRE(a.Lk / BKV <= 64, "attention: Lk=%d exceeds 64 key blocks", a.Lk);
   MSD_REQUIRE(a.nbatch > 0 && a.heads > 0, "attention: empty problem");
   MSD_REQUIRE(a.ldo % 8 == 0, "attention: ldo must be a multiple of 8");
   if (a.mask_bits)
@@ -535,7 +658,12 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   MSD_REQUIRE((a.Lk / BKV) % splits == 0, "attention: %d key blocks not divisible by %d splits",
               a.Lk / BKV, splits);
   d.splits = splits; d.part_o = a.part_o; d.part_ml = a.part_ml;
-  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * splits);
+  int tail = 0;
+  if (splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr && a.tail >= 0)
+    tail = a.tail > 0 ? a.tail : attention_pick_tail(a.nbatch, a.heads, a.Lq, a.Lk);
+  MSD_REQUIRE(tail < a.Lk / BKV, "attention: tail %d must be below %d key blocks", tail, a.Lk / BKV);
+  d.tail = tail; d.nbatch = a.nbatch; d.flags = a.flags; d.kv_static = a.kv_static;
+  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * (tail > 0 ? 2 : splits));
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
   MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, stream,

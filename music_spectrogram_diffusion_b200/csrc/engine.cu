@@ -202,6 +202,7 @@ struct msd_ctx {
   bf16* qc = nullptr;      // [B*N, hh]
   float* attn_part_o = nullptr;   // split-KV partials of the cross-attention [B*N*H*8, 64]
   float* attn_part_ml = nullptr;  // [B*N*H*8, 2]
+  uint32_t* attn_flags = nullptr; // tail-mode hand-shake words, one per softmax warp, kept at 0
   float* eps = nullptr;    // [R, nd]
   float* z = nullptr;      // [B*N*nd]
   bf16* z_split = nullptr; // [B*N, 3*nd]
@@ -521,10 +522,15 @@ static int gemm_pos(const bf16* A, int lda, const bf16* B, int ldb, int M, int N
 static int attention(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv,
                      bf16* O, int ldo, int nb, int H, int Lq, int Lk, const uint32_t* bits,
                      int stride_words, cudaStream_t st, float* part_o = nullptr,
-                     float* part_ml = nullptr) {
+                     float* part_ml = nullptr, uint32_t* flags = nullptr, int kv_static = 0) {
   AttnArgs a;
   memset(&a, 0, sizeof(a));
-  a.part_o = part_o; a.part_ml = part_ml; a.max_splits = 8;
+  a.kv_static = kv_static;
+  a.part_o = part_o; a.part_ml = part_ml; a.max_splits = 8; a.flags = flags;
+  {
+    const char* f = getenv("MSD_ATTN_TAIL");  // tuning / test hook: -1 off, 0 auto, n forced
+    a.tail = f ? atoi(f) : 0;
+  }
   a.Q = Q; a.ldq = ldq; a.K = K; a.ldk = ldk; a.V = V; a.ldv = ldv; a.O = O; a.ldo = ldo;
   a.nbatch = nb; a.heads = H; a.Lq = Lq; a.Lk = Lk; a.mask_bits = bits;
   a.mask_stride_words = stride_words;
@@ -573,7 +579,8 @@ static int decoder_layers_batched(msd_ctx* c, int ncond, int total, cudaStream_t
       MSD_TRY(gemm(c->xn, d, w.cross_q, d, Rc, hh, d, EPI_BF16, c->qc, hh, nullptr, st));
       const bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
       MSD_TRY(attention(c->qc, hh, kv, 2 * hh, kv + hh, 2 * hh, c->attn, hh, ncond, c->H, N, c->Mkv,
-                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml));
+                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml,
+                        c->attn_flags, 1));
       MSD_TRY(gemm(c->attn, hh, w.cross_out, hh, Rc, d, hh, EPI_RESID_F32, c->x, d, c->x, st));
     }
     // MLP block (241-256)
@@ -614,7 +621,8 @@ static int decoder_layers(msd_ctx* c, int seg0, int nseg, bool cross, cudaStream
       MSD_TRY(gemm(xn, d, w.cross_q, d, R, hh, d, EPI_BF16, c->qc, hh, nullptr, st));
       const bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
       MSD_TRY(attention(c->qc, hh, kv, 2 * hh, kv + hh, 2 * hh, attn, hh, nseg, c->H, N, c->Mkv,
-                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml));
+                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml,
+                        c->attn_flags, 1));
       MSD_TRY(gemm(attn, hh, w.cross_out, hh, R, d, hh, EPI_RESID_F32, x, d, x, st));
     }
     // MLP block (241-256)
@@ -637,6 +645,10 @@ static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st,
   const int d = c->d, N = c->N, nd = c->nd;
   const int R = total * N;
   // continuous_inputs_projection + position encodings (420-427); both passes start equal.
+  // The first kernel of a step is a plain (fully dependent) launch: kernels further down read
+  // per-segment constants (cross K/V cache, key mask, step index) ahead of their programmatic
+  // dependency wait, which is only sound if everything before this step has completed.
+  g_pdl_skip_next = true;
   MSD_TRY(gemm_pos(c->z_split, 3 * nd, c->dec_in_proj, 3 * nd, B * N, d, 3 * nd, c->x, c->dec_pos,
                    N, nullptr, total > B ? B * N : 0, st));
   const int nuncond = total - ncond;
@@ -773,6 +785,12 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
     if ((rc = A.alloc(&c->qc, BN * c->hh))) break;
     if ((rc = A.alloc(&c->attn_part_o, BN * c->H * 8 * 64))) break;
     if ((rc = A.alloc(&c->attn_part_ml, BN * c->H * 8 * 2))) break;
+    if ((rc = A.alloc(&c->attn_flags, BN / 32 * c->H + 64))) break;
+    if (cudaMemset(c->attn_flags, 0, (BN / 32 * c->H + 64) * sizeof(uint32_t)) != cudaSuccess) {
+      set_error("msd_create: cudaMemset failed");
+      rc = -2;
+      break;
+    }
     if ((rc = A.alloc(&c->eps, R * c->nd))) break;
     if ((rc = A.alloc(&c->z, BN * c->nd))) break;
     if ((rc = A.alloc(&c->z_split, BN * 3 * c->nd))) break;
@@ -1118,9 +1136,16 @@ int msd_op_attention_trace(const float* q, const float* k, const float* v,
     MSD_TRY(tb.get(&po, static_cast<size_t>(nb) * Lq * heads * 8 * 64));
     MSD_TRY(tb.get(&pml, static_cast<size_t>(nb) * Lq * heads * 8 * 2));
     aa.part_o = po; aa.part_ml = pml; aa.max_splits = 8;
+    uint32_t* fl = nullptr;
+    const size_t nfl = static_cast<size_t>(nb) * heads * ((Lq + 127) / 128) * 4;
+    MSD_TRY(tb.get(&fl, nfl));
+    MSD_CUDA_CHECK(cudaMemsetAsync(fl, 0, nfl * sizeof(uint32_t), st));
+    aa.flags = fl;
     {
       const char* f = getenv("MSD_ATTN_SPLITS");  // test hook: force a split count
       aa.splits = f ? atoi(f) : 0;
+      const char* t = getenv("MSD_ATTN_TAIL");    // test hook: force a tail length (-1 = off)
+      aa.tail = t ? atoi(t) : 0;
     }
     MSD_TRY(launch_attention(aa, st));
   }

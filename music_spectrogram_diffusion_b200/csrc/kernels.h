@@ -125,8 +125,15 @@ struct AttnArgs {
   // split-KV workspace (optional): part_o [rows*heads*max_splits*64] f32, part_ml [..*2] f32;
   // splits 0 = choose automatically (attention_pick_splits), capped by max_splits.
   float* part_o; float* part_ml; int splits; int max_splits;
+  // tail mode (needs part_o / part_ml and a zeroed flags array of nbatch*heads*(Lq/128)*4 words):
+  // tail 0 = choose automatically (attention_pick_tail), > 0 = forced, < 0 = off.
+  uint32_t* flags; int tail;
+  // K, V and mask_bits were written well before the preceding kernel (safe to read ahead of the
+  // programmatic-dependency wait): true for the cross-attention over the per-segment K/V cache.
+  int kv_static;
 };
 int attention_pick_splits(int nbatch, int heads, int Lq, int Lk);
+int attention_pick_tail(int nbatch, int heads, int Lq, int Lk);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int attention_configure();
 

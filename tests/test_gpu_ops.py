@@ -28,6 +28,45 @@ def test_dense_general(cuda_device, M, N, K, variant, block_n):
   assert err < 2e-4 * np.sqrt(K), f'max err {err}'
 
 
+@pytest.mark.parametrize('nb,heads,Lq,Lk,tail,masked', [
+    (2, 2, 128, 256, 1, False), (2, 3, 256, 384, 1, True), (2, 3, 256, 384, 2, True),
+    (1, 2, 256, 2304, 5, True), (2, 2, 256, 768, 2, 'head'), (3, 2, 128, 256, 1, True),
+    (8, 12, 256, 768, 0, False), (8, 12, 256, 2304, 0, True)])
+def test_dot_product_attention_tail_split(cuda_device, monkeypatch, nb, heads, Lq, Lk, tail, masked):
+  """Long/short CTA pairs with the in-kernel merge (tail 0 = the automatic choice, which is active
+  for the 96-CTA grids of the last two cases); run twice to check the hand-shake words re-arm."""
+  from music_spectrogram_diffusion_b200 import engine
+  monkeypatch.setenv('MSD_ATTN_SPLITS', '1')
+  monkeypatch.setenv('MSD_ATTN_TAIL', str(tail))
+  g = torch.Generator().manual_seed(nb * 77 + Lk + tail)
+  w = heads * 64
+  q = bf16_round(torch.randn(nb, Lq, w, generator=g) * 0.5)
+  k = bf16_round(torch.randn(nb, Lk, w, generator=g) * 0.5)
+  v = bf16_round(torch.randn(nb, Lk, w, generator=g))
+  mask = None
+  bias = None
+  if masked:
+    mask = (torch.rand(nb, Lk, generator=g) > 0.3).to(torch.int32)
+    if masked == 'head':
+      mask[0, :Lk - 128] = 0                   # the long CTA of batch 0 has nothing to attend to
+    else:
+      mask[0, Lk // 2:] = 0                    # the short CTA of batch 0 has nothing to attend to
+    if nb > 2:
+      mask[2, :] = 0                           # neither has -> zeros
+    qm = torch.ones(nb, Lq)
+    m4 = O.make_attention_mask(qm, mask.float())
+    bias = torch.where(m4 > 0, torch.zeros_like(m4), torch.full_like(m4, -1e10))
+  want = O.dot_product_attention(q.view(nb, Lq, heads, 64), k.view(nb, Lk, heads, 64),
+                                 v.view(nb, Lk, heads, 64), bias).reshape(nb, Lq, w)
+  if masked:
+    want = O.zero_activations_if_masked(want, m4)
+  for _ in range(2):
+    got = engine.op_attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device),
+                              None if mask is None else mask.to(cuda_device), heads).cpu()
+    err = (got - want).abs().max().item()
+    assert err < 3e-2, f'max err {err}'
+
+
 @pytest.mark.parametrize('splits', [0, 1, 3])
 @pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
     (1, 1, 128, 128, False), (2, 2, 128, 256, False), (2, 3, 256, 384, True),
