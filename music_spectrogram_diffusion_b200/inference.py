@@ -10,9 +10,10 @@ Keeps the reference's call surface:
 and replaces the jitted `predict_batch_with_aux` with libmsd_b200.so (ctypes; torch only
 allocates device/pinned buffers).  There is no CPU fallback.
 
-Checkpoints: `checkpoint_path` may be an `.npz` written by `weights.save_npz` (flax names,
-fp32) or `synthetic:<seed>` (random init; no pretrained checkpoint is available offline).
-Reading T5X/zarr checkpoints directly is future work.
+Checkpoints: `checkpoint_path` may be a T5X checkpoint directory such as
+`.../base_with_context/checkpoint_500000` (msgpack index + one zarr array per parameter, read by
+`t5x_checkpoint.py` without t5x/tensorstore), an `.npz` written by `weights.save_npz` (flax
+names, fp32) or `synthetic:<seed>` (random init; no pretrained checkpoint is available offline).
 
 Noise: `seed` feeds the library's Philox generator.  jax.random's threefry stream is a
 third-party detail that cannot be validated offline, so bit-equality with the reference for a
@@ -29,7 +30,8 @@ from typing import Any, Dict, Mapping, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from music_spectrogram_diffusion_b200 import audio_codecs, config, engine, gin_lite, weights
+from music_spectrogram_diffusion_b200 import (audio_codecs, config, engine, gin_lite, t5x_checkpoint,
+                                              weights)
 
 _GIN_SEARCH_ROOTS = [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))]
 
@@ -232,9 +234,15 @@ class InferenceModel:
                                       self.audio_codec.n_dims, seed=int(cp.split(':', 1)[1]))
     if cp.endswith('.npz'):
       return weights.load_npz(cp)
-    raise NotImplementedError(
-        f'checkpoint {cp!r}: only .npz (weights.save_npz) and synthetic:<seed> are readable; '
-        'the T5X/zarr reader is future work (SURVEY §8f)')
+    if t5x_checkpoint.is_t5x_checkpoint(cp):
+      params = t5x_checkpoint.load_t5x_checkpoint(cp)
+      weights.check_params(params, self.model.module_config, self.inputs_length,
+                           self.targets_length, self.targets_context_length,
+                           self.audio_codec.n_dims)
+      return params
+    raise FileNotFoundError(
+        f'checkpoint {cp!r}: expected a T5X checkpoint directory, an .npz (weights.save_npz) '
+        'or synthetic:<seed>')
 
   def _get_engine(self) -> engine.Engine:
     if self._engine is None:

@@ -5,8 +5,8 @@ Names follow the flax tree the reference creates:
   layer / norm / dense names  network.py:127-152, 174-252, 278-301, 321-355,
                               380-456; msd/layers.py:262-264, 371-377, 485-508
 A real T5X checkpoint flattens to exactly these '/'-joined keys under
-``target/`` (reader is future work); here the tree is either
-synthesised (no checkpoint is available offline) or loaded from an ``.npz``.
+``target/`` (read by ``t5x_checkpoint.py``); the tree can also be synthesised
+(no checkpoint is available offline) or loaded from an ``.npz``.
 """
 
 from __future__ import annotations
@@ -128,6 +128,22 @@ def synthetic_params(cfg: T5Config, inputs_length: int = 2048,
         w = w * 0.1
     out[name] = np.ascontiguousarray(w, dtype=np.float32)
   return out
+
+
+def check_params(params: ParamDict, cfg: T5Config, inputs_length: int, targets_length: int,
+                 context_length: int, n_dims: int = 128) -> None:
+  """Raises if a restored tree lacks a parameter of the inference path or has a wrong shape
+  (the reference fails inside t5x's restore with a shape-mismatch error, inference.py:171-181).
+  Extra entries (optimizer slots, unrelated modules) are ignored."""
+  problems = []
+  for name, shape in param_shapes(cfg, inputs_length, targets_length, context_length, n_dims):
+    if name not in params:
+      problems.append(f'missing {name} {shape}')
+    elif tuple(params[name].shape) != tuple(shape):
+      problems.append(f'{name}: checkpoint shape {tuple(params[name].shape)} != model shape {shape}')
+  if problems:
+    head = '; '.join(problems[:6])
+    raise ValueError(f'checkpoint does not match the gin config ({len(problems)} problems): {head}')
 
 
 def save_npz(path: str, params: ParamDict) -> None:

@@ -156,6 +156,31 @@ def test_inference_model_predict_matches_golden_fixture(cuda_device):
     model.predict(dict(batch, encoder_input_tokens=g['tokens'][:, :64]))
 
 
+def test_inference_model_restores_t5x_checkpoint(cuda_device, tiny, tmp_path):
+  """InferenceModel(checkpoint_path=<T5X directory>, gin_config) -- the colab's call
+  (ipynb:203-229) -- gives bit-identical output to the same tree handed over in memory."""
+  import os
+  from music_spectrogram_diffusion_b200 import inference, t5x_checkpoint
+  t5, params = tiny
+  ck = t5x_checkpoint.save_t5x_checkpoint(str(tmp_path / 'checkpoint_500000'), params, step=500000,
+                                          inline_below=300, chunk_rows=64)
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = 4
+  lengths = {'inputs': T, 'targets': N, 'targets_context': C}
+  a = inference.InferenceModel.from_config(t5, diff, lengths, ck, 1)
+  b = inference.InferenceModel.from_config(t5, diff, lengths, 'synthetic:0', 1, params=params)
+  rng = np.random.default_rng(9)
+  batch = dict(encoder_input_tokens=rng.integers(3, 1391, (1, T)).astype(np.int32),
+               encoder_continuous_inputs=rng.uniform(-11, 4, (1, C, 128)).astype(np.float32),
+               encoder_continuous_mask=np.ones((1, C), np.int32),
+               decoder_target_tokens=np.zeros((1, N, 128), np.float32))
+  ma, _ = a.predict(batch, seed=3)
+  mb, _ = b.predict(batch, seed=3)
+  np.testing.assert_array_equal(ma, mb)
+  with pytest.raises(ValueError, match='does not match the gin config'):
+    inference.InferenceModel.from_config(config.t5_small(), diff, lengths, ck, 1).predict(batch)
+
+
 def test_chained_song_single_gpu(cuda_device, tiny):
   """distributed.synthesize_song on one rank == the colab loop (ipynb:895-935): first segment
   masked context, later ones fed the previous prediction."""
