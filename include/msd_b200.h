@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MSD_B200_ABI_VERSION 1
+#define MSD_B200_ABI_VERSION 2
 
 typedef struct msd_ctx msd_ctx;
 
@@ -46,13 +46,23 @@ typedef struct msd_config {
   int32_t num_steps;             /* sampler schedule num_steps */
   int32_t max_batch;             /* segments per call (B) */
   int32_t sampler;               /* 0 = ddpm, 1 = ddim */
-  int32_t logvar_type;           /* 0 = large, 1 = small (ddpm only) */
+  int32_t logvar_type;           /* 0 = large, 1 = small, 2 = 'medium:<logvar_frac>' (ddpm only) */
   int32_t clip_x0;               /* SamplerConfig.clip_x0 */
   int32_t context_positions;     /* 0 = regular, 1 = terminal_relative */
   float max_decoder_noise_time;  /* T5Config.max_decoder_noise_time (2e4) */
   float eval_condition_weight;   /* classifier-free guidance weight; 1 disables the 2nd pass */
   float feature_min;             /* codec min_value (log 1e-5) */
   float feature_max;             /* codec max_value (4.0) */
+  /* ABI 2: sampler variants of diffusion_utils.py (all 0 = the shipped gin defaults) */
+  int32_t model_output;          /* DiffusionConfig.model_output: 0 eps, 1 x0, 2 v (288-321) */
+  int32_t sampler_schedule;      /* sampler.schedule.name: 0 cosine, 1 linear (166-202) */
+  int32_t train_schedule;        /* train_schedule.name: 0 cosine, 1 linear */
+  int32_t train_num_steps;       /* train_schedule.num_steps (linear only) */
+  float logvar_frac;             /* frac of 'medium:<frac>' (141-156) */
+  float sampler_beta_start;      /* linear sampler schedule: beta range */
+  float sampler_beta_stop;
+  float train_beta_start;        /* linear train schedule: beta range */
+  float train_beta_stop;
 } msd_config;
 
 /* A named fp32 parameter in the reference's own layout (flax tree path joined by '/',
@@ -105,8 +115,12 @@ int msd_decode_eps(msd_ctx* ctx, const float* z, int32_t step_i, int32_t conditi
  * enc_out [B, inputs_length + context_length, emb_dim] device f32. */
 int msd_get_encodings(msd_ctx* ctx, float* enc_out, void* stream);
 
-/* Host copy of the per-step sampler scalars [num_steps][8]:
- * x0_scale, eps_scale, c_z, c_x0, sigma, is_last, logsnr_t, logsnr_s. */
+/* Host copy of the per-step sampler scalars [num_steps][16]:
+ * 0 x0_scale, 1 eps_scale (predict_x0_from_eps at the sampler's logsnr_t), 2 c_z, 3 c_x0,
+ * 4 sigma (ddpm: mean = c_z z + c_x0 x0, std sigma; ddim: 2 = stdv_s, 3 = alpha_s),
+ * 5 is_last, 6 logsnr_t, 7 logsnr_s, 8 p0, 9 p1 (eps = p0 z + p1 model_output, train schedule),
+ * 10 q0, 11 q1 (x0 = q0 z + q1 model_output, train schedule), 12 e1, 13 e2
+ * (predict_eps_from_x0 at logsnr_t: eps = e1 (z - x0 e2)), 14 logsnr_train, 15 reserved. */
 int msd_get_step_table(msd_ctx* ctx, float* table_host);
 
 /* Profiling hook: runs diffusion step `step_i` (1 <= step_i < num_steps) of the batch of the

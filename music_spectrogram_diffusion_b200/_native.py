@@ -87,6 +87,11 @@ class MsdConfig(ctypes.Structure):
       ('max_decoder_noise_time', ctypes.c_float),
       ('eval_condition_weight', ctypes.c_float),
       ('feature_min', ctypes.c_float), ('feature_max', ctypes.c_float),
+      ('model_output', ctypes.c_int32), ('sampler_schedule', ctypes.c_int32),
+      ('train_schedule', ctypes.c_int32), ('train_num_steps', ctypes.c_int32),
+      ('logvar_frac', ctypes.c_float), ('sampler_beta_start', ctypes.c_float),
+      ('sampler_beta_stop', ctypes.c_float), ('train_beta_start', ctypes.c_float),
+      ('train_beta_stop', ctypes.c_float),
   ]
 
 

@@ -167,27 +167,56 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) 
   if (idx >= a.n) return;
   griddep_wait();
   const int step = *a.step;
-  const float* cf = a.coef + static_cast<size_t>(step) * 8;
+  const float* cf = a.coef + static_cast<size_t>(step) * MSD_STEP_COLS;
   const float x0_scale = cf[0], eps_scale = cf[1], c_z = cf[2], c_x0 = cf[3], sigma = cf[4];
   const bool last = cf[5] != 0.f;
+  const float p0 = cf[8], p1 = cf[9], q0 = cf[10], q1 = cf[11], e1 = cf[12], e2 = cf[13];
   const float4 z = *reinterpret_cast<const float4*>(a.z + idx);
-  float4 e = *reinterpret_cast<const float4*>(a.eps + idx);
+  const float4 mo = *reinterpret_cast<const float4*>(a.eps + idx);
+  // _get_x0_and_eps_from_model_output (diffusion_utils.py:288-321): eps = p0 z + p1 out and
+  // x0 = q0 z + q1 out (for model_output == 'eps': p0 = 0, p1 = 1, i.e. eps = out exactly)
+  float4 e, x0;
+  e.x = fmaf(p1, mo.x, p0 * z.x); e.y = fmaf(p1, mo.y, p0 * z.y);
+  e.z = fmaf(p1, mo.z, p0 * z.z); e.w = fmaf(p1, mo.w, p0 * z.w);
+  if (p0 == 0.f && p1 == 1.f) e = mo;
   if (a.passes == 2) {
-    const float4 eu = *reinterpret_cast<const float4*>(a.eps + a.n + idx);
+    // classifier-free guidance on eps, then x0 from the combined eps at logsnr_t (424-433)
+    const float4 mu = *reinterpret_cast<const float4*>(a.eps + a.n + idx);
+    float4 eu;
+    eu.x = fmaf(p1, mu.x, p0 * z.x); eu.y = fmaf(p1, mu.y, p0 * z.y);
+    eu.z = fmaf(p1, mu.z, p0 * z.z); eu.w = fmaf(p1, mu.w, p0 * z.w);
+    if (p0 == 0.f && p1 == 1.f) eu = mu;
     const float w = a.cond_weight, wu = 1.0f - a.cond_weight;
     e.x = w * e.x + wu * eu.x; e.y = w * e.y + wu * eu.y;
     e.z = w * e.z + wu * eu.z; e.w = w * e.w + wu * eu.w;
+    x0.x = x0_scale * (z.x - e.x * eps_scale); x0.y = x0_scale * (z.y - e.y * eps_scale);
+    x0.z = x0_scale * (z.z - e.z * eps_scale); x0.w = x0_scale * (z.w - e.w * eps_scale);
+  } else if (q0 == 0.f && q1 == 1.f) {
+    x0 = mo;
+  } else if (p0 == 0.f && p1 == 1.f) {
+    // predict_x0_from_eps at the train schedule's logsnr: q0 = A, q1 = -A * B
+    const float A = q0, Bc = -q1 / q0;
+    x0.x = A * (z.x - mo.x * Bc); x0.y = A * (z.y - mo.y * Bc);
+    x0.z = A * (z.z - mo.z * Bc); x0.w = A * (z.w - mo.w * Bc);
+  } else {
+    x0.x = fmaf(q1, mo.x, q0 * z.x); x0.y = fmaf(q1, mo.y, q0 * z.y);
+    x0.z = fmaf(q1, mo.z, q0 * z.z); x0.w = fmaf(q1, mo.w, q0 * z.w);
   }
-  float4 x0;
-  x0.x = x0_scale * (z.x - e.x * eps_scale); x0.y = x0_scale * (z.y - e.y * eps_scale);
-  x0.z = x0_scale * (z.z - e.z * eps_scale); x0.w = x0_scale * (z.w - e.w * eps_scale);
   if (a.clip_x0) {
     x0.x = fminf(fmaxf(x0.x, -1.f), 1.f); x0.y = fminf(fmaxf(x0.y, -1.f), 1.f);
     x0.z = fminf(fmaxf(x0.z, -1.f), 1.f); x0.w = fminf(fmaxf(x0.w, -1.f), 1.f);
+    if (a.ddim) {  // pred_eps = predict_eps_from_x0(z, clipped x0, logsnr_t) (437-439)
+      e.x = e1 * (z.x - x0.x * e2); e.y = e1 * (z.y - x0.y * e2);
+      e.z = e1 * (z.z - x0.z * e2); e.w = e1 * (z.w - x0.w * e2);
+    }
   }
   float4 zn;
   if (last) {
     zn = x0;
+  } else if (a.ddim) {
+    // ddim_step (369-379): z_s = alpha_s x0 + stdv_s eps; table columns 3 / 2
+    zn.x = c_x0 * x0.x + c_z * e.x; zn.y = c_x0 * x0.y + c_z * e.y;
+    zn.z = c_x0 * x0.z + c_z * e.z; zn.w = c_x0 * x0.w + c_z * e.w;
   } else {
     float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sigma != 0.f) {

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -190,7 +191,7 @@ struct msd_ctx {
   float* dec_norm = nullptr;
   bf16* spec_out = nullptr;   // [nd, 3*d] split [hi|hi|lo]
   float* film = nullptr;      // [steps, 2*L, 2*d]
-  float* coef = nullptr;      // [steps, 8] device
+  float* coef = nullptr;      // [steps, MSD_STEP_COLS] device
   std::vector<float> coef_host;
 
   // ---- activations (decoder, rows = passes*B*N)
@@ -242,41 +243,101 @@ static float logsnr_cosine(float t) {
   return -2.0f * logf(tanf(arg));
 }
 
+// Linear-beta log-SNR, diffusion_utils.py:189-199: float64 table of
+// log(alphas_cumprod) - log1p(-alphas_cumprod) clipped to [-20, 20], then jnp.interp over
+// linspace(0, 1, num_steps) in float32.
+struct LinearSchedule {
+  std::vector<float> xp, fp;
+  void build(double start, double stop, int n) {
+    xp.resize(n); fp.resize(n);
+    double cum = 1.0;
+    for (int i = 0; i < n; ++i) {
+      const double beta = n > 1 ? start + (stop - start) * static_cast<double>(i) / (n - 1) : start;
+      cum *= 1.0 - beta;
+      double l = log(cum) - log1p(-cum);
+      l = l < -20.0 ? -20.0 : (l > 20.0 ? 20.0 : l);
+      fp[i] = static_cast<float>(l);
+      xp[i] = static_cast<float>(n > 1 ? static_cast<double>(i) / (n - 1) : 0.0);
+    }
+    if (n > 1) xp[n - 1] = 1.0f;
+  }
+  float at(float t) const {
+    const int n = static_cast<int>(xp.size());
+    if (n == 1) return fp[0];
+    if (t < xp[0]) return fp[0];
+    if (t > xp[n - 1]) return fp[n - 1];
+    int i = static_cast<int>(std::upper_bound(xp.begin(), xp.end(), t) - xp.begin());  // side='right'
+    i = i < 1 ? 1 : (i > n - 1 ? n - 1 : i);
+    const float df = fp[i] - fp[i - 1], dx = xp[i] - xp[i - 1], delta = t - xp[i - 1];
+    return dx == 0.f ? fp[i] : fp[i - 1] + (delta / dx) * df;
+  }
+};
+
 static void build_step_table(const msd_config& c, std::vector<float>& tab) {
   const int n = c.num_steps;
-  tab.assign(static_cast<size_t>(n) * 8, 0.f);
+  tab.assign(static_cast<size_t>(n) * MSD_STEP_COLS, 0.f);
+  LinearSchedule lin_s, lin_t;
+  if (c.sampler_schedule == 1) lin_s.build(c.sampler_beta_start, c.sampler_beta_stop, n);
+  if (c.train_schedule == 1) lin_t.build(c.train_beta_start, c.train_beta_stop, c.train_num_steps);
+  auto logsnr_sampler = [&](float t) { return c.sampler_schedule == 1 ? lin_s.at(t) : logsnr_cosine(t); };
+  auto logsnr_train = [&](float t) { return c.train_schedule == 1 ? lin_t.at(t) : logsnr_cosine(t); };
+  auto sigmoidf = [](float v) { return 1.0f / (1.0f + expf(-v)); };
+  auto log_sigmoidf = [](float v) { return v < 0.f ? v - log1pf(expf(v)) : -log1pf(expf(-v)); };
   for (int i = 0; i < n; ++i) {
     const float t = (static_cast<float>(i) + 1.0f) / static_cast<float>(n);
     const float s = static_cast<float>(i) / static_cast<float>(n);
-    const float lt = logsnr_cosine(t), ls = logsnr_cosine(s);
-    float* r = &tab[static_cast<size_t>(i) * 8];
+    const float lt = logsnr_sampler(t), ls = logsnr_sampler(s), ltr = logsnr_train(t);
+    float* r = &tab[static_cast<size_t>(i) * MSD_STEP_COLS];
     // predict_x0_from_eps (215-222): x0 = sqrt(1+e^-lt) * (z - eps * rsqrt(1+e^lt))
     r[0] = sqrtf(1.0f + expf(-lt));
     r[1] = 1.0f / sqrtf(1.0f + expf(lt));
     if (c.sampler == 0) {
       // diffusion_reverse (120-163)
       const float alpha_st = sqrtf((1.0f + expf(-lt)) / (1.0f + expf(-ls)));
-      const float alpha_s = sqrtf(1.0f / (1.0f + expf(-ls)));
+      const float alpha_s = sqrtf(sigmoidf(ls));
       const float rr = expf(lt - ls);
       const float omr = -expm1f(lt - ls);
-      const float var = omr * (c.logvar_type == 0 ? 1.0f / (1.0f + expf(lt))    // sigmoid(-lt)
-                                                  : 1.0f / (1.0f + expf(ls)));  // sigmoid(-ls)
+      float var;
+      if (c.logvar_type == 0) {
+        var = omr * sigmoidf(-lt);
+      } else if (c.logvar_type == 1) {
+        var = omr * sigmoidf(-ls);
+      } else {
+        // log1mexp (100-106) of x = ls - lt > 0, then the log-space interpolation (148-156)
+        const float x = ls - lt;
+        const float l1mr = x > logf(2.0f) ? log1pf(-expf(-x)) : logf(-expm1f(-x));
+        const float min_logvar = l1mr + log_sigmoidf(-ls), max_logvar = l1mr + log_sigmoidf(-lt);
+        var = expf(c.logvar_frac * max_logvar + (1.0f - c.logvar_frac) * min_logvar);
+      }
       r[2] = rr * alpha_st;
       r[3] = omr * alpha_s;
       r[4] = sqrtf(var);
     } else {
-      // ddim_step (369-379): z_s = alpha_s x0 + stdv_s eps', eps' = predict_eps_from_x0(z, x0, lt)
-      const float alpha_s = sqrtf(1.0f / (1.0f + expf(-ls)));
-      const float stdv_s = sqrtf(1.0f / (1.0f + expf(ls)));
-      const float e1 = sqrtf(1.0f + expf(lt));
-      const float e2 = 1.0f / sqrtf(1.0f + expf(-lt));
-      r[2] = stdv_s * e1;
-      r[3] = alpha_s - stdv_s * e1 * e2;
+      // ddim_step (369-379): z_s = alpha_s x0 + stdv_s eps
+      r[2] = sqrtf(sigmoidf(-ls));
+      r[3] = sqrtf(sigmoidf(ls));
       r[4] = 0.0f;
     }
     r[5] = (i == 0) ? 1.0f : 0.0f;
     r[6] = lt;
     r[7] = ls;
+    // _get_x0_and_eps_from_model_output (288-321) at the TRAIN schedule's logsnr(time):
+    // eps = p0 z + p1 out, x0 = q0 z + q1 out
+    const float A = sqrtf(1.0f + expf(-ltr)), Bc = 1.0f / sqrtf(1.0f + expf(ltr));   // x0 from eps
+    const float C = sqrtf(1.0f + expf(ltr)), D = 1.0f / sqrtf(1.0f + expf(-ltr));   // eps from x0
+    if (c.model_output == 0) {
+      r[8] = 0.f; r[9] = 1.f; r[10] = A; r[11] = -A * Bc;
+    } else if (c.model_output == 1) {
+      r[8] = C; r[9] = -C * D; r[10] = 0.f; r[11] = 1.f;
+    } else {
+      const float al = sqrtf(sigmoidf(ltr)), sg = sqrtf(sigmoidf(-ltr));  // x0 = al z - sg v (225-233)
+      r[10] = al; r[11] = -sg;
+      r[8] = C * (1.0f - D * al); r[9] = C * D * sg;
+    }
+    // predict_eps_from_x0 (205-212) at the sampler's logsnr_t
+    r[12] = sqrtf(1.0f + expf(lt));
+    r[13] = 1.0f / sqrtf(1.0f + expf(-lt));
+    r[14] = ltr;
   }
 }
 
@@ -681,7 +742,7 @@ static int sampler_step(msd_ctx* c, int B, const float* noise, unsigned long lon
   a.step = c->d_step; a.mel_out = mel_out;
   a.n = static_cast<long long>(B) * c->N * c->nd;
   a.n_dims = c->nd; a.passes = c->passes; a.cond_weight = c->cfg.eval_condition_weight;
-  a.clip_x0 = c->cfg.clip_x0; a.feat_min = c->cfg.feature_min; a.feat_max = c->cfg.feature_max;
+  a.clip_x0 = c->cfg.clip_x0; a.ddim = c->cfg.sampler == 1; a.feat_min = c->cfg.feature_min; a.feat_max = c->cfg.feature_max;
   a.seed = seed;
   return launch_sampler_step(a, st);
 }
@@ -697,7 +758,15 @@ static int validate(const msd_config* g) {
               "sequence lengths must be multiples of 128");
   MSD_REQUIRE(g->num_steps > 0 && g->max_batch > 0, "num_steps and max_batch must be positive");
   MSD_REQUIRE(g->sampler == 0 || g->sampler == 1, "sampler must be 0 (ddpm) or 1 (ddim)");
-  MSD_REQUIRE(g->logvar_type == 0 || g->logvar_type == 1, "logvar_type must be 0 or 1");
+  MSD_REQUIRE(g->logvar_type >= 0 && g->logvar_type <= 2, "logvar_type must be 0, 1 or 2");
+  MSD_REQUIRE(g->logvar_type != 2 || (g->logvar_frac >= 0.f && g->logvar_frac <= 1.f),
+              "logvar_frac must be in [0, 1]");
+  MSD_REQUIRE(g->model_output >= 0 && g->model_output <= 2, "model_output must be 0 (eps), 1 (x0) or 2 (v)");
+  MSD_REQUIRE((g->sampler_schedule == 0 || g->sampler_schedule == 1) &&
+                  (g->train_schedule == 0 || g->train_schedule == 1),
+              "schedules must be 0 (cosine) or 1 (linear)");
+  MSD_REQUIRE(g->train_schedule == 0 || g->train_num_steps > 0,
+              "linear train schedule needs train_num_steps > 0");
   MSD_REQUIRE(g->vocab_size > 0 && g->num_encoder_layers > 0 && g->num_decoder_layers > 0,
               "bad layer/vocab sizes");
   return 0;
@@ -806,7 +875,7 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
     if ((rc = A.alloc(&c->mask_bits, static_cast<size_t>(c->Bmax) * (c->Mkv / 32)))) break;
     if ((rc = A.alloc(&c->ctx_seq_len, static_cast<size_t>(c->Bmax)))) break;
     if ((rc = A.alloc(&c->d_step, 4))) break;
-    if ((rc = A.alloc(&c->coef, static_cast<size_t>(cfg->num_steps) * 8))) break;
+    if ((rc = A.alloc(&c->coef, static_cast<size_t>(cfg->num_steps) * MSD_STEP_COLS))) break;
     build_step_table(*cfg, c->coef_host);
     if (cudaMemcpy(c->coef, c->coef_host.data(), c->coef_host.size() * sizeof(float),
                    cudaMemcpyHostToDevice) != cudaSuccess) {

@@ -147,12 +147,13 @@ int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* ou
                    const float* film, const int* step, long long film_step_stride,
                    long long film_offset, int split3, cudaStream_t stream);
 
+constexpr int MSD_STEP_COLS = 16;  // floats per diffusion step in the sampler table
 struct SamplerArgs {
   const float* eps;       // [(passes*B)*N, n_dims] rows: cond block then uncond block
   float* z;               // [B*N*n_dims] state, updated in place
   bf16* z_split;          // [B*N, 3*n_dims] = [hi | lo | hi] of the new z
   const float* noise;     // [num_steps, B*N*n_dims] or nullptr -> philox(seed)
-  const float* coef;      // [num_steps, 8]: x0_scale, eps_scale, c_z, c_x0, sigma, last, -, -
+  const float* coef;      // [num_steps, MSD_STEP_COLS], columns documented at msd_get_step_table
   const int* step;        // device step index i
   float* mel_out;         // written when i == 0: scale_to_features(z)
   long long n;            // B*N*n_dims
@@ -160,6 +161,7 @@ struct SamplerArgs {
   int passes;             // 2 with classifier-free guidance, 1 without
   float cond_weight;
   int clip_x0;
+  int ddim;               // 1 = ddim_step, 0 = ddpm_step
   float feat_min, feat_max;
   unsigned long long seed;
 };

@@ -31,13 +31,32 @@ def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int
         'diffusion configs (gin/models/diffusion/context/t5_base.gin:79) is built')
   if t5.decoder_cross_attend_style != 'concat_encodings':
     raise NotImplementedError('only decoder_cross_attend_style="concat_encodings" is built')
-  if diffusion.model_output != 'eps':
-    raise NotImplementedError('only model_output="eps" is built')
-  sched = diffusion.sampler.schedule
-  if sched.name != 'cosine' or diffusion.train_schedule.name != 'cosine':
-    raise NotImplementedError('only the cosine schedule is built')
+  if diffusion.model_output == 'x0_and_eps':
+    raise NotImplementedError(
+        'model_output="x0_and_eps" needs a 2*n_dims output head; the context network emits n_dims '
+        'channels (network.py:452-456), so the reference cannot run it on this path either')
+  if diffusion.model_output not in ('eps', 'x0', 'v'):
+    raise ValueError('Unknown model_output: %s' % diffusion.model_output)
+  sched, tsched = diffusion.sampler.schedule, diffusion.train_schedule
+  names = {'cosine': 0, 'linear': 1}
+  for sc in (sched, tsched):
+    if sc.name not in names:
+      raise ValueError('Schedule %s not identified.' % sc.name)
+    if sc.name == 'linear' and (sc.start is None or sc.stop is None or not sc.num_steps):
+      raise ValueError('linear schedule needs start, stop and num_steps')
+  if diffusion.sampler.name not in ('ddpm', 'ddim'):
+    raise ValueError('Unknown sampler type: %s' % diffusion.sampler.name)
   sampler = {'ddpm': 0, 'ddim': 1}[diffusion.sampler.name]
-  logvar = {'large': 0, 'small': 1}[diffusion.sampler.logvar_type]
+  lv = diffusion.sampler.logvar_type
+  logvar_frac = 0.0
+  if lv.startswith('medium:'):
+    logvar, logvar_frac = 2, float(lv.split(':')[1])
+    if not 0 <= logvar_frac <= 1:
+      raise ValueError(f'logvar_type {lv!r}: frac must be in [0, 1]')
+  elif lv in ('large', 'small'):
+    logvar = {'large': 0, 'small': 1}[lv]
+  else:
+    raise ValueError(f'unknown logvar_type {lv!r}')
   ctxpos = {'regular': 0, 'terminal_relative': 1}[t5.context_positions]
   return _native.MsdConfig(
       vocab_size=t5.vocab_size, emb_dim=t5.emb_dim, num_heads=t5.num_heads,
@@ -49,7 +68,12 @@ def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int
       clip_x0=int(bool(diffusion.sampler.clip_x0)), context_positions=ctxpos,
       max_decoder_noise_time=float(t5.max_decoder_noise_time),
       eval_condition_weight=float(diffusion.classifier_free_guidance.eval_condition_weight),
-      feature_min=float(feature_min), feature_max=float(feature_max))
+      feature_min=float(feature_min), feature_max=float(feature_max),
+      model_output={'eps': 0, 'x0': 1, 'v': 2}[diffusion.model_output],
+      sampler_schedule=names[sched.name], train_schedule=names[tsched.name],
+      train_num_steps=int(tsched.num_steps or 0), logvar_frac=logvar_frac,
+      sampler_beta_start=float(sched.start or 0.0), sampler_beta_stop=float(sched.stop or 0.0),
+      train_beta_start=float(tsched.start or 0.0), train_beta_stop=float(tsched.stop or 0.0))
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
@@ -158,7 +182,7 @@ class Engine:
             for i, name in enumerate(self.KERNEL_CLASSES)}
 
   def step_table(self) -> np.ndarray:
-    tab = np.zeros((self.cfg.num_steps, 8), dtype=np.float32)
+    tab = np.zeros((self.cfg.num_steps, 16), dtype=np.float32)
     _native.check(self.lib.msd_get_step_table(self._h, tab.ctypes.data), 'msd_get_step_table')
     return tab
 

@@ -63,9 +63,14 @@ class OracleConfig:
   context_positions: str = 'terminal_relative'
   # diffusion
   num_steps: int = 1000
-  schedule: str = 'cosine'          # sampler schedule name
+  schedule: str = 'cosine'          # sampler schedule name ('cosine' | 'linear')
+  schedule_start: Optional[float] = None   # linear schedule: beta range
+  schedule_stop: Optional[float] = None
   train_schedule: str = 'cosine'
-  model_output: str = 'eps'
+  train_schedule_start: Optional[float] = None
+  train_schedule_stop: Optional[float] = None
+  train_schedule_num_steps: Optional[int] = None
+  model_output: str = 'eps'         # 'eps' | 'x0' | 'v'
   sampler: str = 'ddpm'
   clip_x0: bool = True
   logvar_type: str = 'large'
@@ -381,17 +386,71 @@ def decode(p: Params, cfg: OracleConfig,
 # -----------------------------------------------------------------------------
 # L3 sampler (msd/models/diffusion/diffusion_utils.py)
 # -----------------------------------------------------------------------------
-def get_logsnr_t(t, schedule: str = 'cosine', dtype=np.float32):
-  """diffusion_utils.py:166-187 (cosine).  a, b are float64 numpy scalars in
-  the reference; `a*t+b` and the log/tan run in the array dtype (float32)."""
+def get_logsnr_t(t, schedule: str = 'cosine', dtype=np.float32, start=None, stop=None,
+                 num_steps=None):
+  """diffusion_utils.py:166-202.  Cosine (181-187): a, b are float64 numpy scalars in the
+  reference; `a*t+b` and the log/tan run in the array dtype (float32).  Linear (189-199):
+  float64 table of log(alphas_cumprod) - log1p(-alphas_cumprod) clipped to [-20, 20], then
+  `jnp.interp` over linspace(0, 1, num_steps) in the array dtype."""
   logsnr_min, logsnr_max = -20.0, 20.0
-  if schedule != 'cosine':
-    raise ValueError('oracle restates the cosine schedule only')
-  b = np.arctan(np.exp(-0.5 * logsnr_max))
-  a = np.arctan(np.exp(-0.5 * logsnr_min)) - b
   t = np.asarray(t, dtype=dtype)
-  arg = (dtype(a) * t + dtype(b)).astype(dtype)
-  return (dtype(-2.0) * np.log(np.tan(arg))).astype(dtype)
+  if schedule == 'cosine':
+    b = np.arctan(np.exp(-0.5 * logsnr_max))
+    a = np.arctan(np.exp(-0.5 * logsnr_min)) - b
+    arg = (dtype(a) * t + dtype(b)).astype(dtype)
+    return (dtype(-2.0) * np.log(np.tan(arg))).astype(dtype)
+  if schedule == 'linear':
+    assert num_steps is not None and num_steps > 0 and start is not None and stop is not None
+    betas = np.linspace(start, stop, num_steps, dtype=np.float64)
+    alphas_cumprod = np.cumprod(1. - betas, axis=0)
+    logsnr = np.log(alphas_cumprod) - np.log1p(-alphas_cumprod)
+    logsnr = np.clip(logsnr, logsnr_min, logsnr_max)
+    xp = np.linspace(0, 1, num_steps).astype(dtype)
+    fp = logsnr.astype(dtype)
+    # jnp.interp: i = clip(searchsorted(xp, x, 'right'), 1, n-1); f = fp[i-1] + (x-xp[i-1])/dx*df
+    i = np.clip(np.searchsorted(xp, t, side='right'), 1, len(xp) - 1)
+    df = fp[i] - fp[i - 1]
+    dx = xp[i] - xp[i - 1]
+    delta = t - xp[i - 1]
+    f = np.where(dx == 0, fp[i], fp[i - 1] + (delta / np.where(dx == 0, dtype(1), dx)) * df)
+    f = np.where(t < xp[0], fp[0], np.where(t > xp[-1], fp[-1], f))
+    return f.astype(dtype)
+  raise ValueError('Schedule %s not identified.' % schedule)
+
+
+def sampler_logsnr(t, cfg: 'OracleConfig', dtype=np.float32):
+  return get_logsnr_t(t, cfg.schedule, dtype, cfg.schedule_start, cfg.schedule_stop, cfg.num_steps)
+
+
+def train_logsnr(t, cfg: 'OracleConfig', dtype=np.float32):
+  return get_logsnr_t(t, cfg.train_schedule, dtype, cfg.train_schedule_start,
+                      cfg.train_schedule_stop, cfg.train_schedule_num_steps)
+
+
+def log1mexp(x: Tensor) -> Tensor:
+  """diffusion_utils.py:100-106: log(1 - exp(-x)) for x > 0."""
+  return torch.where(x > math.log(2.0), torch.log1p(-torch.exp(-x)), torch.log(-torch.expm1(-x)))
+
+
+def predict_x0_from_v(z: Tensor, v: Tensor, logsnr: float) -> Tensor:
+  """diffusion_utils.py:225-233: x0 = alpha z - sigma v."""
+  ls = torch.tensor(logsnr, dtype=z.dtype)
+  return torch.sqrt(torch.sigmoid(ls)) * z - torch.sqrt(torch.sigmoid(-ls)) * v
+
+
+def x0_and_eps_from_model_output(z: Tensor, model_output: Tensor, logsnr: float,
+                                 kind: str) -> Tuple[Tensor, Tensor]:
+  """_get_x0_and_eps_from_model_output, diffusion_utils.py:288-321 (logsnr from the TRAIN
+  schedule).  'x0_and_eps' splits a 2*n_dims output; the context network's spec_out_dense
+  emits n_dims channels (network.py:452-456), so that branch cannot be reached on this path."""
+  if kind == 'eps':
+    return predict_x0_from_eps(z, model_output, logsnr), model_output
+  if kind == 'x0':
+    return model_output, predict_eps_from_x0(z, model_output, logsnr)
+  if kind == 'v':
+    x0 = predict_x0_from_v(z, model_output, logsnr)
+    return x0, predict_eps_from_x0(z, x0, logsnr)
+  raise ValueError('Unknown model_output: %s' % kind)
 
 
 def predict_x0_from_eps(z: Tensor, eps: Tensor, logsnr: float) -> Tensor:
@@ -423,8 +482,15 @@ def diffusion_reverse(x0: Tensor, z_t: Tensor, logsnr_s: float, logsnr_t: float,
     var = one_minus_r * torch.sigmoid(-ls)
   elif logvar_type == 'large':
     var = one_minus_r * torch.sigmoid(-lt)
+  elif logvar_type.startswith('medium:'):
+    frac = float(logvar_type.split(':')[1])
+    assert 0 <= frac <= 1
+    log_one_minus_r = log1mexp(ls - lt)
+    min_logvar = log_one_minus_r + torch.nn.functional.logsigmoid(-ls)
+    max_logvar = log_one_minus_r + torch.nn.functional.logsigmoid(-lt)
+    var = torch.exp(frac * max_logvar + (1 - frac) * min_logvar)
   else:
-    raise ValueError('oracle restates logvar_type small/large only')
+    raise ValueError('unknown logvar_type %s' % logvar_type)
   return {'mean': mean, 'std': torch.sqrt(var), 'var': var}
 
 
@@ -460,21 +526,20 @@ def eval_step(z_t: Tensor, i: int, noise_i: Optional[Tensor], pred_fn: PredFn,
   f32 = np.float32
   t = f32(i + 1.0) / f32(cfg.num_steps)
   s = f32(i) / f32(cfg.num_steps)
-  logsnr_t = float(get_logsnr_t(t, cfg.schedule))
-  logsnr_s = float(get_logsnr_t(s, cfg.schedule))
+  logsnr_t = float(sampler_logsnr(t, cfg))
+  logsnr_s = float(sampler_logsnr(s, cfg))
   batch = z_t.shape[0]
   time = torch.full((batch,), float(t), dtype=z_t.dtype)
 
-  if cfg.model_output != 'eps':
-    raise ValueError('oracle restates model_output == "eps" only')
-  # _get_x0_and_eps_from_model_output (288-300) uses the TRAIN schedule.
-  logsnr_train = float(get_logsnr_t(t, cfg.train_schedule))
-  pred_eps = pred_fn(z_t, time, True)
-  pred_x0 = predict_x0_from_eps(z_t, pred_eps, logsnr_train)
+  # _get_x0_and_eps_from_model_output (288-321) uses the TRAIN schedule.
+  logsnr_train = float(train_logsnr(t, cfg))
+  pred_x0, pred_eps = x0_and_eps_from_model_output(z_t, pred_fn(z_t, time, True), logsnr_train,
+                                                   cfg.model_output)
   if cfg.eval_condition_weight != 1:
     cond_wt = cfg.eval_condition_weight
     uncond_wt = 1. - cond_wt
-    uncond_eps = pred_fn(z_t, time, False)
+    _, uncond_eps = x0_and_eps_from_model_output(z_t, pred_fn(z_t, time, False), logsnr_train,
+                                                 cfg.model_output)
     pred_eps = cond_wt * pred_eps + uncond_wt * uncond_eps
     pred_x0 = predict_x0_from_eps(z_t, pred_eps, logsnr_t)
   if cfg.clip_x0:

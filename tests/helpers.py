@@ -39,12 +39,18 @@ def make_noise(steps, B, N, seed=0):
 
 
 def build_engine(t5, T, N, C, B, steps, cond_weight, params, sampler='ddpm', logvar='large',
-                 clip_x0=True):
+                 clip_x0=True, model_output='eps', schedule=None, train_schedule=None):
+  """schedule / train_schedule: None (cosine) or ('linear', start, stop[, num_steps])."""
   diff = config.DiffusionConfig()
   diff.sampler.schedule.num_steps = steps
   diff.sampler.name = sampler
   diff.sampler.logvar_type = logvar
   diff.sampler.clip_x0 = clip_x0
+  diff.model_output = model_output
+  if schedule is not None:
+    diff.sampler.schedule = config.DiffusionSchedule(schedule[0], schedule[1], schedule[2], steps)
+  if train_schedule is not None:
+    diff.train_schedule = config.DiffusionSchedule(*train_schedule)
   diff.classifier_free_guidance.eval_condition_weight = cond_weight
   eng = engine.Engine(engine.make_msd_config(t5, diff, T, N, C, max_batch=B), 0)
   eng.load_weights(params)

@@ -111,6 +111,62 @@ def test_sample_matches_oracle(cuda_device, tiny, sampler, weight):
   eng.close()
 
 
+VARIANTS = {
+    # name: (engine kwargs, oracle kwargs, cond weight)
+    'ddpm_medium': (dict(logvar='medium:0.3'), dict(logvar_type='medium:0.3'), 2.0),
+    'ddpm_small': (dict(logvar='small'), dict(logvar_type='small'), 2.0),
+    'x0_output': (dict(model_output='x0'), dict(model_output='x0'), 2.0),
+    'v_output': (dict(model_output='v'), dict(model_output='v'), 2.0),
+    'v_output_ddim_noclip_nocfg': (dict(model_output='v', sampler='ddim', clip_x0=False),
+                                   dict(model_output='v', sampler='ddim', clip_x0=False), 1.0),
+    'x0_output_nocfg': (dict(model_output='x0'), dict(model_output='x0'), 1.0),
+    'linear_schedule': (dict(schedule=('linear', 1e-3, 0.3), train_schedule=('linear', 1e-3, 0.3, 12)),
+                        dict(schedule='linear', schedule_start=1e-3, schedule_stop=0.3,
+                             train_schedule='linear', train_schedule_start=1e-3,
+                             train_schedule_stop=0.3, train_schedule_num_steps=12), 2.0),
+    'train_linear_sampler_cosine': (dict(train_schedule=('linear', 1e-4, 0.02, 1000), model_output='x0'),
+                                    dict(train_schedule='linear', train_schedule_start=1e-4,
+                                         train_schedule_stop=0.02, train_schedule_num_steps=1000,
+                                         model_output='x0'), 2.0),
+}
+
+
+@pytest.mark.parametrize('name', sorted(VARIANTS))
+def test_sampler_variants_match_oracle(cuda_device, tiny, name):
+  """The sampler switches of diffusion_utils.py beyond the shipped gin defaults: logvar_type
+  small / medium:<frac> (141-156), model_output x0 / v (301-318), linear schedule (189-199),
+  separate train / sampler schedules, each with identical injected noise against the oracle."""
+  ekw, okw, weight = VARIANTS[name]
+  t5, params = tiny
+  B, steps = 2, 12
+  toks, ctx, cmask = H.make_batch(B, T, C)
+  init_z, noise = H.make_noise(steps, B, N, seed=3)
+  eng = H.build_engine(t5, T, N, C, B, steps, weight, params, **ekw)
+  oc = H.oracle_config(t5, steps, weight, **okw)
+  tab = eng.step_table()
+  for i in (steps - 1, steps // 2, 1):
+    t = np.float32(i + 1.0) / np.float32(steps)
+    s_ = np.float32(i) / np.float32(steps)
+    np.testing.assert_allclose(tab[i][6], O.sampler_logsnr(t, oc), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(tab[i][7], O.sampler_logsnr(s_, oc), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(tab[i][14], O.train_logsnr(t, oc), rtol=2e-4, atol=2e-5)
+    if oc.sampler == 'ddpm':
+      one = torch.ones(1)
+      d = O.diffusion_reverse(one, one, float(tab[i][7]), float(tab[i][6]), oc.logvar_type)
+      np.testing.assert_allclose(tab[i][4], d['std'].item(), rtol=1e-4)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+             b['encoder_continuous_mask'])
+  mel = eng.sample(init_z.to(cuda_device), noise.to(cuda_device)).cpu()
+  ref, _ = O.predict_batch_with_aux(O.params_to(params), oc, H.torch_batch(toks, ctx, cmask),
+                                    init_z, noise)
+  span = oc.max_value - oc.min_value
+  err = (mel - ref).abs() / span * 2.0
+  assert torch.isfinite(mel).all()
+  assert err.mean().item() < 3e-2, f'{name}: mean {err.mean().item()} max {err.max().item()}'
+  eng.close()
+
+
 def test_sample_internal_rng_is_deterministic(cuda_device, tiny):
   t5, params = tiny
   B, steps = 1, 6

@@ -135,14 +135,17 @@ def test_c_abi_exports_every_declared_symbol(native_lib):
   assert declared == bound, (declared ^ bound)
   for name in declared:
     assert hasattr(native_lib, name), name
-  assert native_lib.msd_abi_version() == 1
+  assert native_lib.msd_abi_version() == 2
   assert isinstance(native_lib.msd_last_error(), bytes)
 
 
 def test_struct_layout_matches_header():
-  """msd_config: 17 int32 then 4 float, no padding; msd_tensor: ptr, ptr, int32, int64[4]."""
-  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4
+  """msd_config (ABI 2): 17 int32, 4 float, 4 int32, 5 float, no padding; msd_tensor: ptr, ptr,
+  int32, int64[4]."""
+  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4 + 4 * 4 + 5 * 4
   assert _native.MsdConfig.max_decoder_noise_time.offset == 68
+  assert _native.MsdConfig.model_output.offset == 84
+  assert _native.MsdConfig.logvar_frac.offset == 100
   assert ctypes.sizeof(_native.MsdTensor) == 8 + 8 + 8 + 32
   assert _native.MsdTensor.shape.offset == 24
 
@@ -152,3 +155,39 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
   monkeypatch.setattr(_native, 'LIB_PATH', str(tmp_path / 'nope.so'))
   with pytest.raises(_native.MsdError, match='no CPU fallback'):
     _native.load()
+
+
+def test_unreachable_sampler_settings_are_refused():
+  from music_spectrogram_diffusion_b200 import engine
+  t5 = config.t5_tiny()
+  for mutate, exc in ((lambda d: setattr(d, 'model_output', 'x0_and_eps'), NotImplementedError),
+                      (lambda d: setattr(d, 'model_output', 'w'), ValueError),
+                      (lambda d: setattr(d.sampler, 'logvar_type', 'medium:1.5'), ValueError),
+                      (lambda d: setattr(d.sampler, 'name', 'euler'), ValueError),
+                      (lambda d: setattr(d.sampler.schedule, 'name', 'sigmoid'), ValueError),
+                      (lambda d: setattr(d.train_schedule, 'name', 'linear'), ValueError)):
+    diff = config.DiffusionConfig()
+    mutate(diff)
+    with pytest.raises(exc):
+      engine.make_msd_config(t5, diff, 128, 128, 128, max_batch=1)
+
+
+def test_gin_bindings_reach_the_sampler_variants():
+  """gin overrides of diffusion_utils.{SamplerConfig, DiffusionConfig, DiffusionSchedule} map to
+  the ABI-2 fields of msd_config."""
+  gin_config = inference.parse_training_gin_file(GIN, [
+      "diffusion_utils.SamplerConfig.logvar_type = 'medium:0.25'",
+      "diffusion_utils.SamplerConfig.name = 'ddpm'",
+      "diffusion_utils.DiffusionConfig.model_output = 'v'",
+      "sampler/diffusion_utils.DiffusionSchedule.name = 'linear'",
+      "sampler/diffusion_utils.DiffusionSchedule.start = 1e-4",
+      "sampler/diffusion_utils.DiffusionSchedule.stop = 0.02",
+      "sampler/diffusion_utils.DiffusionSchedule.num_steps = 250",
+  ])
+  m = inference.InferenceModel('synthetic:0', gin_config, batch_size=1)
+  d = m.model.diffusion_config
+  assert d.sampler.schedule.name == 'linear' and d.sampler.schedule.num_steps == 250
+  cfg = engine.make_msd_config(m.model.module_config, d, 2048, 256, 256, 1)
+  assert (cfg.logvar_type, cfg.model_output, cfg.sampler_schedule, cfg.train_schedule) == (2, 2, 1, 0)
+  assert abs(cfg.logvar_frac - 0.25) < 1e-7 and cfg.num_steps == 250
+  assert abs(cfg.sampler_beta_start - 1e-4) < 1e-9 and abs(cfg.sampler_beta_stop - 0.02) < 1e-8

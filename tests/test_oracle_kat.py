@@ -148,3 +148,52 @@ def test_get_sequence_length_and_roll():
   assert O.get_sequence_length(torch.tensor([1, 1, 1])) == 3
   assert O.get_sequence_length(torch.tensor([0, 0, 0])) == 0
   assert torch.roll(torch.arange(5), 2, 0).tolist() == [3, 4, 0, 1, 2]
+
+
+def test_linear_schedule_matches_float64_interp():
+  """diffusion_utils.py:189-199 restated in float32 against a float64 numpy evaluation."""
+  n, start, stop = 1000, 1e-4, 0.02
+  betas = np.linspace(start, stop, n, dtype=np.float64)
+  ac = np.cumprod(1. - betas)
+  table = np.clip(np.log(ac) - np.log1p(-ac), -20.0, 20.0)
+  ts = np.array([0.0, 1e-3, 0.25, 0.5, 0.7512, 0.999, 1.0])
+  want = np.interp(ts, np.linspace(0, 1, n), table)
+  got = O.get_logsnr_t(ts, 'linear', np.float32, start, stop, n)
+  np.testing.assert_allclose(got, want, rtol=3e-4, atol=3e-4)
+  assert got[0] == np.float32(table[0]) and got[-1] == np.float32(table[-1])
+  with pytest.raises(ValueError, match='not identified'):
+    O.get_logsnr_t(0.5, 'sigmoid')
+
+
+def test_medium_logvar_interpolates_between_small_and_large():
+  """diffusion_utils.py:141-156: frac 0 == 'small', frac 1 == 'large', log-linear in between."""
+  one = torch.ones(3, dtype=torch.float64)
+  ls, lt = 1.7, 0.4
+  small = O.diffusion_reverse(one, one, ls, lt, 'small')['var']
+  large = O.diffusion_reverse(one, one, ls, lt, 'large')['var']
+  np.testing.assert_allclose(O.diffusion_reverse(one, one, ls, lt, 'medium:0')['var'], small, rtol=1e-12)
+  np.testing.assert_allclose(O.diffusion_reverse(one, one, ls, lt, 'medium:1')['var'], large, rtol=1e-12)
+  mid = O.diffusion_reverse(one, one, ls, lt, 'medium:0.25')['var']
+  np.testing.assert_allclose(mid, large ** 0.25 * small ** 0.75, rtol=1e-12)
+  x = torch.tensor([1e-3, 0.3, 0.7, 5.0], dtype=torch.float64)
+  np.testing.assert_allclose(O.log1mexp(x), np.log(1 - np.exp(-x.numpy())), rtol=1e-10)
+
+
+def test_model_output_conversions_are_consistent():
+  """diffusion_utils.py:205-233, 288-321: x0 / eps / v describe the same point."""
+  g = torch.Generator().manual_seed(0)
+  z = torch.randn(4, 8, dtype=torch.float64, generator=g)
+  eps = torch.randn(4, 8, dtype=torch.float64, generator=g)
+  ls = -0.8
+  x0, e = O.x0_and_eps_from_model_output(z, eps, ls, 'eps')
+  assert e is eps
+  x0b, eb = O.x0_and_eps_from_model_output(z, x0, ls, 'x0')
+  np.testing.assert_allclose(eb, eps, rtol=1e-10)
+  alpha, sigma = np.sqrt(1 / (1 + np.exp(-ls))), np.sqrt(1 / (1 + np.exp(ls)))
+  np.testing.assert_allclose(alpha * x0 + sigma * eps, z, rtol=1e-10)   # z = alpha x0 + sigma eps
+  v = alpha * eps - sigma * x0
+  x0c, ec = O.x0_and_eps_from_model_output(z, v, ls, 'v')
+  np.testing.assert_allclose(x0c, x0, rtol=1e-9)
+  np.testing.assert_allclose(ec, eps, rtol=1e-9)
+  with pytest.raises(ValueError, match='Unknown model_output'):
+    O.x0_and_eps_from_model_output(z, eps, ls, 'x0_and_eps')
