@@ -649,17 +649,27 @@ int gemm_configure() {
 // divide N.  74 clusters run concurrently; a tile costs ~BN cycles per k-step.
 int gemm_pick_pair_bn(int M, int N) {
   // Measured on B200 (tools/gemm_bench.py): the widest tile wins (least L2->SM traffic per FLOP)
-  // unless it leaves clusters idle that a 192-wide tiling would use.
+  // unless it leaves clusters idle that a narrower tiling would use: among the widths whose tile
+  // count fits the 74 concurrently running clusters, take the one with the most tiles.
   const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  if (N % 256 == 0) {
-    const int t256 = m_pairs * (N / 256);
-    if (N % 192 == 0 && t256 < 74 && m_pairs * (N / 192) > t256) return 192;
-    return 256;
+  static const bool small_m_rule = [] {
+    const char* e = getenv("MSD_GEMM_TILE_RULE");  // tuning hook: 0 = only 256 / 192 compete
+    return !(e && e[0] == '0');
+  }();
+  const int widths[4] = {256, 192, 128, 64};
+  int best = 0, best_tiles = 0;
+  for (int i = 0; i < (small_m_rule ? 4 : 2); ++i) {
+    const int bn = widths[i];
+    if (N % bn != 0) continue;
+    const int tiles = m_pairs * (N / bn);
+    if (best == 0) { best = bn; best_tiles = tiles; continue; }   // widest dividing width
+    if (best_tiles < 74 && tiles <= 74 && tiles > best_tiles) { best = bn; best_tiles = tiles; }
   }
-  if (N % 192 == 0) return 192;
-  if (N % 128 == 0) return 128;
-  if (N % 64 == 0) return 64;
-  return 0;
+  if (best == 0) {
+    for (int i = 0; i < 4; ++i)
+      if (N % widths[i] == 0) return widths[i];
+  }
+  return best;
 }
 
 int gemm_pick_block_n(int M, int N) {
