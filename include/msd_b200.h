@@ -63,6 +63,8 @@ typedef struct msd_config {
   float sampler_beta_stop;
   float train_beta_start;        /* linear train schedule: beta range */
   float train_beta_stop;
+  int32_t cross_attend_style;    /* T5Config.decoder_cross_attend_style: 0 concat_encodings,
+                                    1 sum_cross_attends (network.py:199-216) */
 } msd_config;
 
 /* A named fp32 parameter in the reference's own layout (flax tree path joined by '/',

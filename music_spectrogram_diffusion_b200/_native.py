@@ -91,7 +91,7 @@ class MsdConfig(ctypes.Structure):
       ('train_schedule', ctypes.c_int32), ('train_num_steps', ctypes.c_int32),
       ('logvar_frac', ctypes.c_float), ('sampler_beta_start', ctypes.c_float),
       ('sampler_beta_stop', ctypes.c_float), ('train_beta_start', ctypes.c_float),
-      ('train_beta_stop', ctypes.c_float),
+      ('train_beta_stop', ctypes.c_float), ('cross_attend_style', ctypes.c_int32),
   ]
 
 

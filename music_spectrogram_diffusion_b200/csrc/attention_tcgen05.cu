@@ -57,6 +57,7 @@ struct AttnDev {
   // their short partner before the final store.  Balances grids that fill 50-100 % of the SMs.
   int tail, nbatch;
   int kv_static;    // K, V and mask_bits are not produced by the preceding kernels (see TMA warp)
+  int kv_batch_rows, kv_row0;  // K/V row of (batch b, key block j) = b*kv_batch_rows + kv_row0 + j*128
   uint32_t* flags;  // [nbatch * heads * q-tiles * 4] one per softmax warp, 0 outside a launch
 };
 
@@ -205,8 +206,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t ph = (it / KV_STAGES) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&kv_full[s], 2 * KV_TILE_BYTES);
-        tma_load_2d(sK + s * KV_TILE_BYTES, &tmap_k, &kv_full[s], head * HD, b * p.Lk + jb * BKV);
-        tma_load_2d(sV + s * KV_TILE_BYTES, &tmap_v, &kv_full[s], head * HD, b * p.Lk + jb * BKV);
+        const int krow = b * p.kv_batch_rows + p.kv_row0 + jb * BKV;
+        tma_load_2d(sK + s * KV_TILE_BYTES, &tmap_k, &kv_full[s], head * HD, krow);
+        tma_load_2d(sV + s * KV_TILE_BYTES, &tmap_v, &kv_full[s], head * HD, krow);
         ++it;
       };
       if (p.kv_static) {
@@ -643,10 +645,15 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   const int width = a.heads * HD;
   if (a.tmap_q) tq = *a.tmap_q;
   else if (int rc = make_tmap_bf16_2d(&tq, a.Q, (uint64_t)a.nbatch * a.Lq, width, a.ldq, BQ)) return rc;
+  const int kv_batch_rows = a.kv_batch_rows > 0 ? a.kv_batch_rows : a.Lk;
+  MSD_REQUIRE(a.kv_row0 >= 0 && a.kv_row0 + a.Lk <= kv_batch_rows,
+              "attention: key rows [%d, %d) exceed the %d rows per batch", a.kv_row0, a.kv_row0 + a.Lk,
+              kv_batch_rows);
+  const uint64_t kv_rows = (uint64_t)a.nbatch * kv_batch_rows;
   if (a.tmap_k) tk = *a.tmap_k;
-  else if (int rc = make_tmap_bf16_2d(&tk, a.K, (uint64_t)a.nbatch * a.Lk, width, a.ldk, BKV)) return rc;
+  else if (int rc = make_tmap_bf16_2d(&tk, a.K, kv_rows, width, a.ldk, BKV)) return rc;
   if (a.tmap_v) tv = *a.tmap_v;
-  else if (int rc = make_tmap_bf16_2d(&tv, a.V, (uint64_t)a.nbatch * a.Lk, width, a.ldv, BKV)) return rc;
+  else if (int rc = make_tmap_bf16_2d(&tv, a.V, kv_rows, width, a.ldv, BKV)) return rc;
   AttnDev d;
   d.O = a.O; d.ldo = a.ldo; d.heads = a.heads; d.Lq = a.Lq; d.Lk = a.Lk;
   d.mask_bits = a.mask_bits; d.mask_stride_words = a.mask_stride_words;
@@ -663,6 +670,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     tail = a.tail > 0 ? a.tail : attention_pick_tail(a.nbatch, a.heads, a.Lq, a.Lk);
   MSD_REQUIRE(tail < a.Lk / BKV, "attention: tail %d must be below %d key blocks", tail, a.Lk / BKV);
   d.tail = tail; d.nbatch = a.nbatch; d.flags = a.flags; d.kv_static = a.kv_static;
+  d.kv_batch_rows = kv_batch_rows; d.kv_row0 = a.kv_row0;
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * (tail > 0 ? 2 : splits));
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);

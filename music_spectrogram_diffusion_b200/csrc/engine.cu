@@ -155,9 +155,13 @@ struct DecLayer {
   float* ln_cross = nullptr;
   float* ln_mlp = nullptr;
   AttnWeights self_attn;
-  bf16* cross_q = nullptr;   // [hh, d]
-  bf16* cross_kv = nullptr;  // [2*hh, d]  (key | value rows)
-  bf16* cross_out = nullptr; // [d, hh]
+  // concat_encodings: one attention over [tokens | context]; sum_cross_attends: one per source
+  // with q stacked along N ([2*hh, d]) and out stacked along K ([d, 2*hh]) so that both sources
+  // still cost one projection GEMM each way.
+  bf16* cross_q = nullptr;    // [hh, d] | [2*hh, d]
+  bf16* cross_kv = nullptr;   // [2*hh, d]  (key | value rows), source 0 (tokens) or both
+  bf16* cross_kv1 = nullptr;  // [2*hh, d]  source 1 (context), sum_cross_attends only
+  bf16* cross_out = nullptr;  // [d, hh] | [d, 2*hh]
   MlpWeights mlp;
 };
 struct Encoder {
@@ -200,7 +204,8 @@ struct msd_ctx {
   bf16* qkv = nullptr;     // [R, 3*hh]
   bf16* attn = nullptr;    // [R, hh]
   bf16* hmid = nullptr;    // [R, F]
-  bf16* qc = nullptr;      // [B*N, hh]
+  bf16* qc = nullptr;      // [B*N, hh] (sum_cross_attends: [B*N, 2*hh])
+  bf16* attn2 = nullptr;   // [B*N, 2*hh] outputs of the two cross-attentions (sum_cross_attends)
   float* attn_part_o = nullptr;   // split-KV partials of the cross-attention [B*N*H*8, 64]
   float* attn_part_ml = nullptr;  // [B*N*H*8, 2]
   uint32_t* attn_flags = nullptr; // tail-mode hand-shake words, one per softmax warp, kept at 0
@@ -498,14 +503,19 @@ static int load_all(msd_ctx* c, Loader& L) {
     MSD_TRY(load_f32(L, A, p + "/pre_self_attention_layer_norm/scale", d, 1, &dl.ln_self));
     MSD_TRY(load_attn(L, A, p + "/self_attention", d, hh, &dl.self_attn));
     MSD_TRY(load_f32(L, A, p + "/pre_cross_attention_layer_norm/scale", d, 1, &dl.ln_cross));
-    const std::string x = p + "/MultiHeadDotProductAttention_0";
-    MSD_TRY(A.alloc(&dl.cross_q, static_cast<size_t>(hh) * d));
+    const int nsrc = g.cross_attend_style == 1 ? 2 : 1;
+    MSD_TRY(A.alloc(&dl.cross_q, static_cast<size_t>(nsrc) * hh * d));
     MSD_TRY(A.alloc(&dl.cross_kv, static_cast<size_t>(2) * hh * d));
-    MSD_TRY(A.alloc(&dl.cross_out, static_cast<size_t>(d) * hh));
-    MSD_TRY(pack_into(L, x + "/query/kernel", d, hh, dl.cross_q, d, 0, 0, 0));
-    MSD_TRY(pack_into(L, x + "/key/kernel", d, hh, dl.cross_kv, d, 0, 0, 0));
-    MSD_TRY(pack_into(L, x + "/value/kernel", d, hh, dl.cross_kv, d, hh, 0, 0));
-    MSD_TRY(pack_into(L, x + "/out/kernel", hh, d, dl.cross_out, hh, 0, 0, 0));
+    if (nsrc == 2) MSD_TRY(A.alloc(&dl.cross_kv1, static_cast<size_t>(2) * hh * d));
+    MSD_TRY(A.alloc(&dl.cross_out, static_cast<size_t>(d) * nsrc * hh));
+    for (int sidx = 0; sidx < nsrc; ++sidx) {
+      const std::string x = p + "/MultiHeadDotProductAttention_" + std::to_string(sidx);
+      bf16* kvw = sidx == 0 ? dl.cross_kv : dl.cross_kv1;
+      MSD_TRY(pack_into(L, x + "/query/kernel", d, hh, dl.cross_q, d, sidx * hh, 0, 0));
+      MSD_TRY(pack_into(L, x + "/key/kernel", d, hh, kvw, d, 0, 0, 0));
+      MSD_TRY(pack_into(L, x + "/value/kernel", d, hh, kvw, d, hh, 0, 0));
+      MSD_TRY(pack_into(L, x + "/out/kernel", hh, d, dl.cross_out, nsrc * hh, 0, sidx * hh, 0));
+    }
     MSD_TRY(load_f32(L, A, p + "/pre_mlp_layer_norm/scale", d, 1, &dl.ln_mlp));
     MSD_TRY(load_mlp(L, A, p + "/mlp", d, F, &dl.mlp));
   }
@@ -583,10 +593,11 @@ static int gemm_pos(const bf16* A, int lda, const bf16* B, int ldb, int M, int N
 static int attention(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv,
                      bf16* O, int ldo, int nb, int H, int Lq, int Lk, const uint32_t* bits,
                      int stride_words, cudaStream_t st, float* part_o = nullptr,
-                     float* part_ml = nullptr, uint32_t* flags = nullptr, int kv_static = 0) {
+                     float* part_ml = nullptr, uint32_t* flags = nullptr, int kv_static = 0,
+                     int kv_batch_rows = 0, int kv_row0 = 0) {
   AttnArgs a;
   memset(&a, 0, sizeof(a));
-  a.kv_static = kv_static;
+  a.kv_static = kv_static; a.kv_batch_rows = kv_batch_rows; a.kv_row0 = kv_row0;
   a.part_o = part_o; a.part_ml = part_ml; a.max_splits = 8; a.flags = flags;
   {
     const char* f = getenv("MSD_ATTN_TAIL");  // tuning / test hook: -1 off, 0 auto, n forced
@@ -618,6 +629,34 @@ static int run_encoder(msd_ctx* c, const Encoder& e, int B, int len, const uint3
   return 0;
 }
 
+// Cross-attention block of a DecoderLayer (network.py:196-235) over `nseg` conditioned segments:
+// rows x / xn (scratch) / attn (scratch, [rows, hh]).  concat_encodings attends the concatenated
+// [tokens | context] cache once; sum_cross_attends runs one attention per source (each zeroed
+// where its source is fully masked) and sums them inside the stacked output projection.
+static int cross_attention_block(msd_ctx* c, const DecLayer& w, int l, float* x, bf16* xn, bf16* attn,
+                                 int nseg, cudaStream_t st) {
+  const int d = c->d, hh = c->hh, N = c->N, R = nseg * N;
+  MSD_TRY(launch_rmsnorm(x, w.ln_cross, R, d, xn, d, nullptr, nullptr, 0, 0, 0, st));
+  const bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
+  if (c->cfg.cross_attend_style == 0) {
+    MSD_TRY(gemm(xn, d, w.cross_q, d, R, hh, d, EPI_BF16, c->qc, hh, nullptr, st));
+    MSD_TRY(attention(c->qc, hh, kv, 2 * hh, kv + hh, 2 * hh, attn, hh, nseg, c->H, N, c->Mkv,
+                      c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml,
+                      c->attn_flags, 1));
+    MSD_TRY(gemm(attn, hh, w.cross_out, hh, R, d, hh, EPI_RESID_F32, x, d, x, st));
+    return 0;
+  }
+  MSD_TRY(gemm(xn, d, w.cross_q, d, R, 2 * hh, d, EPI_BF16, c->qc, 2 * hh, nullptr, st));
+  MSD_TRY(attention(c->qc, 2 * hh, kv, 2 * hh, kv + hh, 2 * hh, c->attn2, 2 * hh, nseg, c->H, N,
+                    c->T, c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml,
+                    c->attn_flags, 1, c->Mkv, 0));
+  MSD_TRY(attention(c->qc + hh, 2 * hh, kv, 2 * hh, kv + hh, 2 * hh, c->attn2 + hh, 2 * hh, nseg,
+                    c->H, N, c->C, c->mask_bits + c->T / 32, c->Mkv / 32, st, c->attn_part_o,
+                    c->attn_part_ml, c->attn_flags, 1, c->Mkv, c->T));
+  MSD_TRY(gemm(c->attn2, 2 * hh, w.cross_out, 2 * hh, R, d, 2 * hh, EPI_RESID_F32, x, d, x, st));
+  return 0;
+}
+
 // Single-chain variant: conditional + unconditional rows batched in every kernel except the
 // cross-attention block (used by the profiler and when MSD_TWO_STREAMS=0).
 static int decoder_layers_batched(msd_ctx* c, int ncond, int total, cudaStream_t st) {
@@ -635,15 +674,7 @@ static int decoder_layers_batched(msd_ctx* c, int ncond, int total, cudaStream_t
                       total, c->H, N, N, nullptr, 0, st));
     MSD_TRY(gemm(c->attn, hh, w.self_attn.out, hh, R, d, hh, EPI_RESID_F32, c->x, d, c->x, st));
     // cross-attention block (196-235), conditioned rows only
-    if (Rc > 0) {
-      MSD_TRY(launch_rmsnorm(c->x, w.ln_cross, Rc, d, c->xn, d, nullptr, nullptr, 0, 0, 0, st));
-      MSD_TRY(gemm(c->xn, d, w.cross_q, d, Rc, hh, d, EPI_BF16, c->qc, hh, nullptr, st));
-      const bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
-      MSD_TRY(attention(c->qc, hh, kv, 2 * hh, kv + hh, 2 * hh, c->attn, hh, ncond, c->H, N, c->Mkv,
-                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml,
-                        c->attn_flags, 1));
-      MSD_TRY(gemm(c->attn, hh, w.cross_out, hh, Rc, d, hh, EPI_RESID_F32, c->x, d, c->x, st));
-    }
+    if (Rc > 0) MSD_TRY(cross_attention_block(c, w, l, c->x, c->xn, c->attn, ncond, st));
     // MLP block (241-256)
     MSD_TRY(launch_rmsnorm(c->x, w.ln_mlp, R, d, c->xn, d, c->film, c->d_step, fstride,
                            static_cast<long long>(2 * l + 1) * 2 * d, 0, st));
@@ -677,15 +708,7 @@ static int decoder_layers(msd_ctx* c, int seg0, int nseg, bool cross, cudaStream
                       N, nullptr, 0, st));
     MSD_TRY(gemm(attn, hh, w.self_attn.out, hh, R, d, hh, EPI_RESID_F32, x, d, x, st));
     // cross-attention block (196-235), conditioned rows only (they are segments [0, ncond))
-    if (cross) {
-      MSD_TRY(launch_rmsnorm(x, w.ln_cross, R, d, xn, d, nullptr, nullptr, 0, 0, 0, st));
-      MSD_TRY(gemm(xn, d, w.cross_q, d, R, hh, d, EPI_BF16, c->qc, hh, nullptr, st));
-      const bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
-      MSD_TRY(attention(c->qc, hh, kv, 2 * hh, kv + hh, 2 * hh, attn, hh, nseg, c->H, N, c->Mkv,
-                        c->mask_bits, c->Mkv / 32, st, c->attn_part_o, c->attn_part_ml,
-                        c->attn_flags, 1));
-      MSD_TRY(gemm(attn, hh, w.cross_out, hh, R, d, hh, EPI_RESID_F32, x, d, x, st));
-    }
+    if (cross) MSD_TRY(cross_attention_block(c, w, l, x, xn, attn, nseg, st));
     // MLP block (241-256)
     MSD_TRY(launch_rmsnorm(x, w.ln_mlp, R, d, xn, d, c->film, c->d_step, fstride,
                            static_cast<long long>(2 * l + 1) * 2 * d, 0, st));
@@ -765,6 +788,8 @@ static int validate(const msd_config* g) {
   MSD_REQUIRE((g->sampler_schedule == 0 || g->sampler_schedule == 1) &&
                   (g->train_schedule == 0 || g->train_schedule == 1),
               "schedules must be 0 (cosine) or 1 (linear)");
+  MSD_REQUIRE(g->cross_attend_style == 0 || g->cross_attend_style == 1,
+              "cross_attend_style must be 0 (concat_encodings) or 1 (sum_cross_attends)");
   MSD_REQUIRE(g->train_schedule == 0 || g->train_num_steps > 0,
               "linear train schedule needs train_num_steps > 0");
   MSD_REQUIRE(g->vocab_size > 0 && g->num_encoder_layers > 0 && g->num_decoder_layers > 0,
@@ -851,7 +876,8 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
     if ((rc = A.alloc(&c->qkv, R * 3 * c->hh))) break;
     if ((rc = A.alloc(&c->attn, R * c->hh))) break;
     if ((rc = A.alloc(&c->hmid, R * c->F))) break;
-    if ((rc = A.alloc(&c->qc, BN * c->hh))) break;
+    if ((rc = A.alloc(&c->qc, BN * c->hh * (cfg->cross_attend_style == 1 ? 2 : 1)))) break;
+    if (cfg->cross_attend_style == 1 && (rc = A.alloc(&c->attn2, BN * 2 * c->hh))) break;
     if ((rc = A.alloc(&c->attn_part_o, BN * c->H * 8 * 64))) break;
     if ((rc = A.alloc(&c->attn_part_ml, BN * c->H * 8 * 2))) break;
     if ((rc = A.alloc(&c->attn_flags, BN / 32 * c->H + 64))) break;
@@ -976,8 +1002,19 @@ int msd_encode(msd_ctx* c, const int32_t* tokens, const float* ctx_features,
   // cross-attention K/V of every decoder layer, once per segment batch
   for (int l = 0; l < c->cfg.num_decoder_layers; ++l) {
     bf16* kv = c->kv_cache + static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
-    MSD_TRY(gemm(c->enc, d, c->dec[l].cross_kv, d, B * c->Mkv, 2 * hh, d, EPI_BF16, kv, 2 * hh,
-                 nullptr, st));
+    if (c->cfg.cross_attend_style == 0) {
+      MSD_TRY(gemm(c->enc, d, c->dec[l].cross_kv, d, B * c->Mkv, 2 * hh, d, EPI_BF16, kv, 2 * hh,
+                   nullptr, st));
+      continue;
+    }
+    // sum_cross_attends: each source has its own key / value kernels; same cache layout
+    for (int b = 0; b < B; ++b) {
+      const size_t r0 = static_cast<size_t>(b) * c->Mkv;
+      MSD_TRY(gemm(c->enc + r0 * d, d, c->dec[l].cross_kv, d, c->T, 2 * hh, d, EPI_BF16,
+                   kv + r0 * 2 * hh, 2 * hh, nullptr, st));
+      MSD_TRY(gemm(c->enc + (r0 + c->T) * d, d, c->dec[l].cross_kv1, d, c->C, 2 * hh, d, EPI_BF16,
+                   kv + (r0 + c->T) * 2 * hh, 2 * hh, nullptr, st));
+    }
   }
   c->cur_batch = B;
   MSD_TRY(end_on(c, caller));

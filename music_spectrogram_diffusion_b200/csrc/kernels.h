@@ -131,6 +131,9 @@ struct AttnArgs {
   // K, V and mask_bits were written well before the preceding kernel (safe to read ahead of the
   // programmatic-dependency wait): true for the cross-attention over the per-segment K/V cache.
   int kv_static;
+  // K/V rows of batch b, key block j start at b * kv_batch_rows + kv_row0 + j * 128
+  // (kv_batch_rows 0 = Lk): lets one source of a concatenated [tokens | context] cache be attended.
+  int kv_batch_rows, kv_row0;
 };
 int attention_pick_splits(int nbatch, int heads, int Lq, int Lk);
 int attention_pick_tail(int nbatch, int heads, int Lq, int Lk);

@@ -29,8 +29,9 @@ def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int
     raise NotImplementedError(
         f'mlp_activations={t5.mlp_activations}: only the gated-GELU MLP of the '
         'diffusion configs (gin/models/diffusion/context/t5_base.gin:79) is built')
-  if t5.decoder_cross_attend_style != 'concat_encodings':
-    raise NotImplementedError('only decoder_cross_attend_style="concat_encodings" is built')
+  styles = {'concat_encodings': 0, 'sum_cross_attends': 1}
+  if t5.decoder_cross_attend_style not in styles:
+    raise ValueError(f'Unknown decoder_cross_attend_style: {t5.decoder_cross_attend_style}')
   if diffusion.model_output == 'x0_and_eps':
     raise NotImplementedError(
         'model_output="x0_and_eps" needs a 2*n_dims output head; the context network emits n_dims '
@@ -73,7 +74,8 @@ def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int
       sampler_schedule=names[sched.name], train_schedule=names[tsched.name],
       train_num_steps=int(tsched.num_steps or 0), logvar_frac=logvar_frac,
       sampler_beta_start=float(sched.start or 0.0), sampler_beta_stop=float(sched.stop or 0.0),
-      train_beta_start=float(tsched.start or 0.0), train_beta_stop=float(tsched.stop or 0.0))
+      train_beta_start=float(tsched.start or 0.0), train_beta_stop=float(tsched.stop or 0.0),
+      cross_attend_style=styles[t5.decoder_cross_attend_style])
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:

@@ -15,6 +15,7 @@ def oracle_config(t5, steps, cond_weight, **kw):
       vocab_size=t5.vocab_size, emb_dim=t5.emb_dim, num_heads=t5.num_heads,
       num_encoder_layers=t5.num_encoder_layers, num_decoder_layers=t5.num_decoder_layers,
       head_dim=t5.head_dim, mlp_dim=t5.mlp_dim, num_steps=steps,
+      decoder_cross_attend_style=t5.decoder_cross_attend_style,
       eval_condition_weight=cond_weight, **kw)
 
 

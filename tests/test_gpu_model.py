@@ -167,6 +167,40 @@ def test_sampler_variants_match_oracle(cuda_device, tiny, name):
   eng.close()
 
 
+def test_sum_cross_attends_matches_oracle(cuda_device):
+  """decoder_cross_attend_style='sum_cross_attends' (network.py:199-216): one attention per
+  encoder with its own kernels, each zeroed where its source is fully masked, outputs summed."""
+  t5 = config.t5_tiny()
+  t5.decoder_cross_attend_style = 'sum_cross_attends'
+  params = weights.synthetic_params(t5, T, N, C, seed=5)
+  assert 'decoder/layers_0/MultiHeadDotProductAttention_1/key/kernel' in params
+  B, steps = 3, 8
+  toks, ctx, cmask = H.make_batch(B, T, C, ctx_masks=[1, 0, 1])   # segment 1: context fully masked
+  cmask[2, 40:] = 0
+  init_z, noise = H.make_noise(steps, B, N, seed=2)
+  eng = H.build_engine(t5, T, N, C, B, steps, 2.0, params)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'], b['encoder_continuous_mask'])
+  oc = H.oracle_config(t5, steps, 2.0)
+  assert oc.decoder_cross_attend_style == 'sum_cross_attends'
+  # one conditioned decoder forward ...
+  z = init_z.to(cuda_device)
+  eps = eng.decode_eps(z, steps - 1, True).cpu()
+  p = O.params_to(params)
+  cb = H.torch_batch(toks, ctx, cmask)
+  encs = O.encode(p, oc, cb['encoder_input_tokens'],
+                  O.scale_features(cb['encoder_continuous_inputs'], oc, clip=True),
+                  cb['encoder_continuous_mask'])
+  want = O.decode(p, oc, encs, init_z, torch.full((B,), 1.0))
+  assert _rel(eps, want) < 3e-2
+  # ... and the whole trajectory
+  mel = eng.sample(z, noise.to(cuda_device)).cpu()
+  ref, _ = O.predict_batch_with_aux(p, oc, cb, init_z, noise)
+  err = (mel - ref).abs() / (oc.max_value - oc.min_value) * 2.0
+  assert torch.isfinite(mel).all() and err.mean().item() < 3e-2, (err.mean().item(), err.max().item())
+  eng.close()
+
+
 def test_sample_internal_rng_is_deterministic(cuda_device, tiny):
   t5, params = tiny
   B, steps = 1, 6
@@ -235,6 +269,32 @@ def test_inference_model_restores_t5x_checkpoint(cuda_device, tiny, tmp_path):
   np.testing.assert_array_equal(ma, mb)
   with pytest.raises(ValueError, match='does not match the gin config'):
     inference.InferenceModel.from_config(config.t5_small(), diff, lengths, ck, 1).predict(batch)
+
+
+def test_song_driver_end_to_end(cuda_device, tiny):
+  """song.synthesize_song (notes -> tokens -> chained predict) on the real engine equals the
+  same chain driven by hand through InferenceModel.predict."""
+  from music_spectrogram_diffusion_b200 import inference, midi_tokens as M, song
+  t5, params = tiny
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = 5
+  diff.classifier_free_guidance.eval_condition_weight = 2.0
+  lengths = {'inputs': T, 'targets': N, 'targets_context': C}
+  model = inference.InferenceModel.from_config(t5, diff, lengths, 'synthetic:0', 1, params=params)
+  notes = M.make_notes([(0.2, 4.0, 60, 100, 0, False), (1.0, 1.3, 38, 110, 0, True),
+                        (3.0, 3.4, 67, 80, 41, False)])
+  out = song.synthesize_song(model, notes, seed=4)
+  nseg = -(-M.num_song_frames(4.0) // N)
+  assert nseg == 2 and out['full_pred_encoded'].shape == (nseg * N, 128)
+  assert np.isfinite(out['full_pred_encoded']).all()
+  assert out['model_timing']['prediction_seconds_per_chunk'] > 0
+  prev = np.zeros((1, C, 128), np.float32)
+  for i in range(nseg):
+    batch = dict(encoder_input_tokens=out['tokens'][i:i + 1], encoder_continuous_inputs=prev,
+                 encoder_continuous_mask=np.full((1, C), 0 if i == 0 else 1, np.int32),
+                 decoder_target_tokens=np.zeros((1, N, 128), np.float32))
+    prev, _ = model.predict(batch, seed=4)
+    np.testing.assert_array_equal(out['full_pred_encoded'][i * N:(i + 1) * N], prev[0])
 
 
 def test_chained_song_single_gpu(cuda_device, tiny):

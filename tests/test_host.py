@@ -86,7 +86,9 @@ def test_unsupported_configs_fail_loudly():
     engine.make_msd_config(t5, d, 2048, 256, 256, 1)
   t5 = config.t5_base()
   t5.decoder_cross_attend_style = 'sum_cross_attends'
-  with pytest.raises(NotImplementedError):
+  assert engine.make_msd_config(t5, d, 2048, 256, 256, 1).cross_attend_style == 1
+  t5.decoder_cross_attend_style = 'product'
+  with pytest.raises(ValueError, match='Unknown decoder_cross_attend_style'):
     engine.make_msd_config(t5, d, 2048, 256, 256, 1)
 
 
@@ -140,9 +142,10 @@ def test_c_abi_exports_every_declared_symbol(native_lib):
 
 
 def test_struct_layout_matches_header():
-  """msd_config (ABI 2): 17 int32, 4 float, 4 int32, 5 float, no padding; msd_tensor: ptr, ptr,
-  int32, int64[4]."""
-  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4 + 4 * 4 + 5 * 4
+  """msd_config (ABI 2): 17 int32, 4 float, 4 int32, 5 float, 1 int32, no padding; msd_tensor:
+  ptr, ptr, int32, int64[4]."""
+  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4 + 4 * 4 + 5 * 4 + 4
+  assert _native.MsdConfig.cross_attend_style.offset == 120
   assert _native.MsdConfig.max_decoder_noise_time.offset == 68
   assert _native.MsdConfig.model_output.offset == 84
   assert _native.MsdConfig.logvar_frac.offset == 100
