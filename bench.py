@@ -274,6 +274,34 @@ def peaks():
   return 1400.0, 6650.0, 'fallback'
 
 
+def single_song_sample(t5, diff, lengths, device_index, segments=3):
+  """BASELINE config 5 in miniature on one GPU: one synthetic multi-instrument song, segments
+  chained through song.synthesize_song (batch 1, context = previous prediction), timed like the
+  reference's `model_timing` (first segment excluded, beam/evaluation.py:217-220)."""
+  from music_spectrogram_diffusion_b200 import inference, midi_tokens, song
+  model = inference.InferenceModel.from_config(t5, diff, lengths, 'synthetic:0', 1, device_index)
+  rng = np.random.default_rng(5)
+  seconds = segments * lengths['targets'] / FRAME_RATE - 0.25
+  rows = []
+  for program in (0, 25, 33, 48, 56):
+    t = float(rng.uniform(0, 0.3))
+    while t < seconds - 0.3:
+      d = float(rng.uniform(0.1, 0.9))
+      rows.append((t, min(t + d, seconds), int(rng.integers(36, 84)), int(rng.integers(30, 127)),
+                   program, False))
+      t += float(rng.uniform(0.08, 0.4))
+  out = song.synthesize_song(model, midi_tokens.make_notes(rows), seed=0)
+  timing = out['model_timing']
+  del model
+  return {
+      'segments': int(len(out['tokens'])), 'notes': len(rows),
+      'tokens_per_segment': [int((r > 0).sum()) for r in out['tokens']],
+      'seconds_per_segment': timing['prediction_seconds_per_chunk'],
+      'x_realtime': 1.0 / timing['predictions_seconds_per_audio_second'],
+      'api': 'song.synthesize_song(InferenceModel(batch_size=1), notes): tokenise + chained predict',
+  }
+
+
 def run_ours(args):
   import torch
   import torch.distributed as dist
@@ -362,7 +390,7 @@ def run_ours(args):
       with open(tpath) as f:
         traffic = json.load(f).get('dram_bytes_per_launch')
     roofline = {
-        'kernel': 'gemm_bf16_tcgen05_kernel', 'bound': 'tensor',
+        'kernel': 'gemm_bf16_tcgen05_pair_kernel', 'bound': 'tensor',
         'achieved': gemm_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
         'frac': gemm_tf / peak_tf, 'peak_source': f'{peak_kind} (bf16 sustained)',
         'traffic': traffic,
@@ -397,6 +425,8 @@ def run_ours(args):
         'kernel_classes_ms_per_diffusion_step': {k: round(v['ms'], 4) for k, v in prof.items()},
         'attention_tflops': attn_tf,
     }
+    if world == 1 and not args.no_song and lengths['inputs'] >= 2048:
+      line['single_song'] = single_song_sample(t5, diff, lengths, local)
     if world == 1 and not args.no_cpu_baseline:
       cores = best_thread_count(t5, diff, lengths)
       t_enc, t_step = cpu_oracle_sample(t5, diff, lengths, args.cpu_steps, cores)
@@ -427,6 +457,8 @@ def main():
   ap.add_argument('--cpu-steps', type=int, default=2,
                   help='diffusion steps in the bounded CPU sample')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-song', action='store_true',
+                  help='skip the batch-1 chained-song sample (BASELINE config 5 in miniature)')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

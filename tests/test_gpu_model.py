@@ -201,6 +201,32 @@ def test_sum_cross_attends_matches_oracle(cuda_device):
   eng.close()
 
 
+def test_tail_split_inside_the_step_graph(cuda_device, monkeypatch):
+  """B = 8 base-sized cross-attention (96 CTAs) runs in long/short CTA pairs inside the captured
+  step graph; the hand-shake words must re-arm across layers and steps.  Compared with the same
+  engine built with the split disabled (same math, different summation order)."""
+  t5 = config.t5_small()
+  Ts, Ns, Cs, B, steps = 2048, 256, 256, 13, 3          # 13 x 6 heads = 78 CTAs, 18 key blocks
+  params = weights.synthetic_params(t5, Ts, Ns, Cs, seed=2)
+  toks, ctx, cmask = H.make_batch(B, Ts, Cs, seed=8, pad_second=True)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  outs = []
+  for tail in ('-1', '0'):
+    monkeypatch.setenv('MSD_ATTN_TAIL', tail)
+    eng = H.build_engine(t5, Ts, Ns, Cs, B, steps, 2.0, params)
+    eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+               b['encoder_continuous_mask'])
+    outs.append([eng.sample(seed=3).clone(), eng.sample(seed=3).clone()])
+    eng.close()
+  (plain, plain2), (split, split2) = outs
+  assert torch.equal(plain, plain2) and torch.equal(split, split2)       # deterministic, re-armed
+  span = 4.0 - np.log(1e-5)
+  err = (plain - split).abs() / span * 2.0
+  assert torch.isfinite(split).all()
+  assert err.mean().item() < 2e-3, (err.mean().item(), err.max().item())
+  assert not torch.equal(plain, split)                                   # the split really ran
+
+
 def test_sample_internal_rng_is_deterministic(cuda_device, tiny):
   t5, params = tiny
   B, steps = 1, 6

@@ -13,7 +13,7 @@ def main():
       k, v = kv.split('=')
       env[k] = v
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '2', '--warmup', '1',
-                          '--no-cpu-baseline', '--diffusion-steps', '300', '--segments',
+                          '--no-cpu-baseline', '--no-song', '--diffusion-steps', '300', '--segments',
                           env.get('SWEEP_SEGMENTS', '8')], env=env, cwd=ROOT,
                          capture_output=True, text=True, timeout=600)
     line = [l for l in out.stdout.splitlines() if l.startswith('{')]
