@@ -586,16 +586,30 @@ attention_combine_kernel(const float* __restrict__ part_o, const float* __restri
 
 }  // namespace
 
+// SMs of the current device (148 on B200).  The long/short split below relies on every short CTA
+// finding an SM that no long CTA occupies, so the real count is used, not the nominal one.
+static int device_sm_count() {
+  static const int sms = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    return n;
+  }();
+  return sms;
+}
+
 int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
   const int nkb = Lk / BKV;
   // measured on B200: splitting pays only when fewer than half the SMs would be busy (B = 8
   // cross-attention, 96 CTAs, is no faster split 3-way: per-CTA fixed costs eat the gain)
-  if (ctas >= 74 || nkb < 6) return 1;
+  const int sms = device_sm_count();
+  if (ctas >= sms / 2 || nkb < 6) return 1;
   int best = 1;
   for (int s = 2; s <= 8; ++s) {
     if (nkb % s != 0 || nkb / s < 3) continue;  // >= 3 key blocks per CTA keeps the prologue small
-    if (ctas * s <= 2 * 148) best = s;
+    if (ctas * s <= 2 * sms) best = s;
   }
   return best;
 }
@@ -606,7 +620,7 @@ int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
 int attention_pick_tail(int nbatch, int heads, int Lq, int Lk) {
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
   const int nkb = Lk / BKV;
-  const int sms = 148;
+  const int sms = device_sm_count();
   if (ctas < sms / 2 || ctas >= sms || nkb < 6) return 0;
   const int free_sms = sms - ctas;
   const int rounds = (ctas + free_sms - 1) / free_sms;
@@ -669,6 +683,13 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr && a.tail >= 0)
     tail = a.tail > 0 ? a.tail : attention_pick_tail(a.nbatch, a.heads, a.Lq, a.Lk);
   MSD_REQUIRE(tail < a.Lk / BKV, "attention: tail %d must be below %d key blocks", tail, a.Lk / BKV);
+  if (tail > 0) {
+    // long CTAs wait for their short partners: every long CTA must be resident together with at
+    // least one SM left for the short ones, or the wait could never end
+    const int longs = ((a.Lq + 2 * BQ - 1) / (2 * BQ)) * a.heads * a.nbatch;
+    MSD_REQUIRE(longs < device_sm_count(), "attention: tail split needs fewer long CTAs (%d) than SMs (%d)",
+                longs, device_sm_count());
+  }
   d.tail = tail; d.nbatch = a.nbatch; d.flags = a.flags; d.kv_static = a.kv_static;
   d.kv_batch_rows = kv_batch_rows; d.kv_row0 = a.kv_row0;
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * (tail > 0 ? 2 : splits));
