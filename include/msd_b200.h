@@ -65,6 +65,10 @@ typedef struct msd_config {
   float train_beta_stop;
   int32_t cross_attend_style;    /* T5Config.decoder_cross_attend_style: 0 concat_encodings,
                                     1 sum_cross_attends (network.py:199-216) */
+  int32_t rng_kind;              /* noise when msd_sample gets no init_z / noise: 0 = Philox4x32-10
+                                    (library stream), 1 = jax.random threefry2x32 stream of
+                                    PRNGKey(seed) / fold_in(key, i) (inference.py:203,
+                                    diffusion_utils.py:389-390, 462) */
 } msd_config;
 
 /* A named fp32 parameter in the reference's own layout (flax tree path joined by '/',
@@ -171,6 +175,11 @@ int msd_op_attention_trace(const float* q, const float* k, const float* v,
  * scale|bias vector film [2*d] (NULL = none): out f32 (bf16-rounded) [rows, d]. */
 int msd_op_rmsnorm_film(const float* x, const float* gamma, const float* film, int32_t rows,
                         int32_t d, float* out, void* stream);
+
+/* jax.random.normal of the sampler's stream: step < 0 -> normal(PRNGKey(seed), [n]) (init_z,
+ * diffusion_utils.py:462), else normal(fold_in(PRNGKey(seed), step), [n]) (389-390).
+ * out: device f32 [n], n a multiple of 8.  Test hook for the rng_kind = 1 generator. */
+int msd_op_jax_normal(uint64_t seed, int32_t step, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,7 @@ class MsdConfig(ctypes.Structure):
       ('logvar_frac', ctypes.c_float), ('sampler_beta_start', ctypes.c_float),
       ('sampler_beta_stop', ctypes.c_float), ('train_beta_start', ctypes.c_float),
       ('train_beta_stop', ctypes.c_float), ('cross_attend_style', ctypes.c_int32),
+      ('rng_kind', ctypes.c_int32),
   ]
 
 
@@ -125,6 +126,7 @@ SYMBOLS = [
     ('msd_op_attention', ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     ('msd_op_attention_trace', ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     ('msd_op_rmsnorm_film', ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P]),
+    ('msd_op_jax_normal', ctypes.c_int, [ctypes.c_uint64, _I, ctypes.c_int64, _P, _P]),
 ]
 
 _lib: Optional[ctypes.CDLL] = None

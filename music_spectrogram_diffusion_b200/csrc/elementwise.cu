@@ -158,6 +158,73 @@ __device__ __forceinline__ void store_split4(bf16* zs, long long idx, int n_dims
 }
 
 // ---------------------------------------------------------------------------
+// jax.random (threefry2x32) noise, restated from the published algorithm (jax 0.3.16 defaults;
+// CPU twin and derivation: music_spectrogram_diffusion_b200/jax_rng.py).  Element e of an
+// n-element draw is word e of threefry_2x32(key, arange(n)): the counters are split into halves,
+// so e < n/2 is the first output word of the pair (e, e + n/2) and e >= n/2 the second word of
+// (e - n/2, e).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint2 threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    const int r0 = (g & 1) ? 17 : 13, r1 = (g & 1) ? 29 : 15, r2 = (g & 1) ? 16 : 26, r3 = (g & 1) ? 24 : 6;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r0) ^ x0;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r1) ^ x0;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r2) ^ x0;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r3) ^ x0;
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + static_cast<uint32_t>(g + 1);
+  }
+  return make_uint2(x0, x1);
+}
+
+// XLA's float32 erfinv (Giles' two single-precision polynomials in w = -log1p(-x^2))
+__device__ __forceinline__ float erfinv_xla(float x) {
+  const float w = -log1pf(-x * x);
+  float p;
+  if (w < 5.0f) {
+    const float v = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = 3.43273939e-07f + p * v; p = -3.5233877e-06f + p * v; p = -4.39150654e-06f + p * v;
+    p = 0.00021858087f + p * v; p = -0.00125372503f + p * v; p = -0.00417768164f + p * v;
+    p = 0.246640727f + p * v; p = 1.50140941f + p * v;
+  } else {
+    const float v = sqrtf(w) - 3.0f;
+    p = -0.000200214257f;
+    p = 0.000100950558f + p * v; p = 0.00134934322f + p * v; p = -0.00367342844f + p * v;
+    p = 0.00573950773f + p * v; p = -0.0076224613f + p * v; p = 0.00943887047f + p * v;
+    p = 1.00167406f + p * v; p = 2.83297682f + p * v;
+  }
+  return p * x;
+}
+
+__device__ __forceinline__ float jax_normal_from_bits(uint32_t bits) {
+  const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  const float lo = -0.99999994f;                       // nextafter(-1, 0); (1 - lo) rounds to 2
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, 2.0f), lo));
+  return 1.41421354f * erfinv_xla(u);
+}
+
+// normals for elements [4*i4, 4*i4 + 4) of an n-element draw (n a multiple of 8)
+__device__ __forceinline__ float4 jax_normal4(const uint32_t* key, long long n, long long i4) {
+  const uint32_t k0 = key[0], k1 = key[1];
+  const long long half = n >> 1, e = i4 * 4;
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long ej = e + j;
+    const bool second = ej >= half;
+    const uint32_t c0 = static_cast<uint32_t>(second ? ej - half : ej);
+    const uint2 o = threefry2x32(k0, k1, c0, static_cast<uint32_t>(c0 + half));
+    r[j] = jax_normal_from_bits(second ? o.y : o.x);
+  }
+  return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// ---------------------------------------------------------------------------
 // One reverse-diffusion update (CFG combine + x0 + clip + DDPM/DDIM mean + noise)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) {
@@ -223,8 +290,10 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) 
       if (a.noise != nullptr) {
         nz = *reinterpret_cast<const float4*>(a.noise + static_cast<size_t>(step) * a.n + idx);
       } else {
-        nz = philox_normal4(a.seed, static_cast<uint32_t>(step) + 1u,
-                            static_cast<unsigned long long>(i4));
+        nz = a.rng_kind == 1
+                 ? jax_normal4(a.rng_keys + 2 * (step + 1), a.n, i4)
+                 : philox_normal4(a.seed, static_cast<uint32_t>(step) + 1u,
+                                  static_cast<unsigned long long>(i4));
       }
     }
     zn.x = c_z * z.x + c_x0 * x0.x + sigma * nz.x; zn.y = c_z * z.y + c_x0 * x0.y + sigma * nz.y;
@@ -250,12 +319,13 @@ __global__ void step_advance_kernel(int* step) {
 
 __global__ void __launch_bounds__(256)
 init_z_kernel(const float* init_z, float* z, bf16* zs, long long n, int n_dims,
-              unsigned long long seed) {
+              unsigned long long seed, int rng_kind, const uint32_t* rng_keys) {
   const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long idx = i4 * 4;
   if (idx >= n) return;
   float4 v;
   if (init_z != nullptr) v = *reinterpret_cast<const float4*>(init_z + idx);
+  else if (rng_kind == 1) v = jax_normal4(rng_keys, n, i4);
   else v = philox_normal4(seed, 0u, static_cast<unsigned long long>(i4));
   *reinterpret_cast<float4*>(z + idx) = v;
   store_split4(zs, idx, n_dims, v);
@@ -481,9 +551,28 @@ int launch_step_advance(int* step, cudaStream_t stream) {
   return 0;
 }
 
+__global__ void __launch_bounds__(256)
+jax_normal_kernel(uint32_t k0, uint32_t k1, long long n, float* out) {
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  const uint32_t key[2] = {k0, k1};
+  *reinterpret_cast<float4*>(out + i4 * 4) = jax_normal4(key, n, i4);
+}
+
+int launch_jax_normal(uint32_t k0, uint32_t k1, long long n, float* out, cudaStream_t stream) {
+  MSD_REQUIRE(n > 0 && n % 8 == 0 && n < (1ll << 32), "jax_normal: n must be k*8 < 2^32");
+  jax_normal_kernel<<<blocks_for(n / 4, 256), 256, 0, stream>>>(k0, k1, n, out);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int launch_init_z(const float* init_z, float* z, bf16* z_split, long long n, int n_dims,
-                  unsigned long long seed, cudaStream_t stream) {
-  init_z_kernel<<<blocks_for(n / 4, 256), 256, 0, stream>>>(init_z, z, z_split, n, n_dims, seed);
+                  unsigned long long seed, cudaStream_t stream, int rng_kind,
+                  const uint32_t* rng_keys) {
+  MSD_REQUIRE(rng_kind == 0 || (rng_keys != nullptr && n % 8 == 0 && n < (1ll << 32)),
+              "init_z: the jax stream needs its key table and a draw of k*8 < 2^32 elements");
+  init_z_kernel<<<blocks_for(n / 4, 256), 256, 0, stream>>>(init_z, z, z_split, n, n_dims, seed,
+                                                            rng_kind, rng_keys);
   MSD_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;

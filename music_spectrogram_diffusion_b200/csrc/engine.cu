@@ -196,6 +196,8 @@ struct msd_ctx {
   bf16* spec_out = nullptr;   // [nd, 3*d] split [hi|hi|lo]
   float* film = nullptr;      // [steps, 2*L, 2*d]
   float* coef = nullptr;      // [steps, MSD_STEP_COLS] device
+  uint32_t* rng_keys = nullptr;  // [steps + 1, 2] jax.random keys of the current seed (rng_kind 1)
+  unsigned long long rng_keys_seed = ~0ull;
   std::vector<float> coef_host;
 
   // ---- activations (decoder, rows = passes*B*N)
@@ -277,6 +279,24 @@ struct LinearSchedule {
     return dx == 0.f ? fp[i] : fp[i - 1] + (delta / dx) * df;
   }
 };
+
+// Threefry-2x32, 20 rounds (host twin of the device function in elementwise.cu)
+static void threefry2x32_host(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  static const int rot[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0];
+  x1 += ks[1];
+  for (int g = 0; g < 5; ++g) {
+    for (int j = 0; j < 4; ++j) {
+      x0 += x1;
+      x1 = ((x1 << rot[g & 1][j]) | (x1 >> (32 - rot[g & 1][j]))) ^ x0;
+    }
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + static_cast<uint32_t>(g + 1);
+  }
+  out[0] = x0;
+  out[1] = x1;
+}
 
 static void build_step_table(const msd_config& c, std::vector<float>& tab) {
   const int n = c.num_steps;
@@ -766,7 +786,7 @@ static int sampler_step(msd_ctx* c, int B, const float* noise, unsigned long lon
   a.n = static_cast<long long>(B) * c->N * c->nd;
   a.n_dims = c->nd; a.passes = c->passes; a.cond_weight = c->cfg.eval_condition_weight;
   a.clip_x0 = c->cfg.clip_x0; a.ddim = c->cfg.sampler == 1; a.feat_min = c->cfg.feature_min; a.feat_max = c->cfg.feature_max;
-  a.seed = seed;
+  a.seed = seed; a.rng_kind = c->cfg.rng_kind; a.rng_keys = c->rng_keys;
   return launch_sampler_step(a, st);
 }
 
@@ -788,6 +808,7 @@ static int validate(const msd_config* g) {
   MSD_REQUIRE((g->sampler_schedule == 0 || g->sampler_schedule == 1) &&
                   (g->train_schedule == 0 || g->train_schedule == 1),
               "schedules must be 0 (cosine) or 1 (linear)");
+  MSD_REQUIRE(g->rng_kind == 0 || g->rng_kind == 1, "rng_kind must be 0 (philox) or 1 (jax threefry)");
   MSD_REQUIRE(g->cross_attend_style == 0 || g->cross_attend_style == 1,
               "cross_attend_style must be 0 (concat_encodings) or 1 (sum_cross_attends)");
   MSD_REQUIRE(g->train_schedule == 0 || g->train_num_steps > 0,
@@ -902,6 +923,13 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
     if ((rc = A.alloc(&c->ctx_seq_len, static_cast<size_t>(c->Bmax)))) break;
     if ((rc = A.alloc(&c->d_step, 4))) break;
     if ((rc = A.alloc(&c->coef, static_cast<size_t>(cfg->num_steps) * MSD_STEP_COLS))) break;
+    if ((rc = A.alloc(&c->rng_keys, (static_cast<size_t>(cfg->num_steps) + 1) * 2))) break;
+    if (cudaMemset(c->rng_keys, 0, (static_cast<size_t>(cfg->num_steps) + 1) * 2 * sizeof(uint32_t)) !=
+        cudaSuccess) {
+      set_error("msd_create: cudaMemset failed");
+      rc = -2;
+      break;
+    }
     build_step_table(*cfg, c->coef_host);
     if (cudaMemcpy(c->coef, c->coef_host.data(), c->coef_host.size() * sizeof(float),
                    cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1065,14 +1093,27 @@ int msd_sample(msd_ctx* c, const float* init_z, const float* noise, uint64_t see
   cudaStream_t st = c->work;
   const int B = c->cur_batch, steps = c->cfg.num_steps;
   const long long n = static_cast<long long>(B) * c->N * c->nd;
-  MSD_TRY(launch_init_z(init_z, c->z, c->z_split, n, c->nd, seed, st));
+  if (c->cfg.rng_kind == 1 && c->rng_keys_seed != seed) {
+    // PRNGKey(seed) and fold_in(key, i) for every scan index (host threefry, 8 KB upload); the
+    // captured step graph reads the table, so a new seed does not force a re-capture
+    std::vector<uint32_t> keys(2 * (static_cast<size_t>(steps) + 1));
+    keys[0] = static_cast<uint32_t>(seed >> 32);
+    keys[1] = static_cast<uint32_t>(seed);
+    for (int i = 0; i < steps; ++i)
+      threefry2x32_host(keys[0], keys[1], 0u, static_cast<uint32_t>(i), &keys[2 * (i + 1)]);
+    MSD_CUDA_CHECK(cudaMemcpyAsync(c->rng_keys, keys.data(), keys.size() * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, st));
+    MSD_CUDA_CHECK(cudaStreamSynchronize(st));
+    c->rng_keys_seed = seed;
+  }
+  MSD_TRY(launch_init_z(init_z, c->z, c->z_split, n, c->nd, seed, st, c->cfg.rng_kind, c->rng_keys));
   const int first = steps - 1;
   MSD_CUDA_CHECK(cudaMemcpyAsync(c->d_step, &first, sizeof(int), cudaMemcpyHostToDevice, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));  // `first` is a stack variable
   // One diffusion step == one graph launch; the step index lives in device memory so the same
   // executable graph serves all num_steps iterations.
   if (c->graph_exec == nullptr || c->graph_batch != B || c->graph_noise != noise ||
-      c->graph_mel != mel_out || c->graph_seed != seed) {
+      c->graph_mel != mel_out || (c->cfg.rng_kind == 0 && c->graph_seed != seed)) {
     drop_graph(c);
     const unsigned long long before = g_launch_count;
     cudaGraph_t graph = nullptr;
@@ -1256,6 +1297,21 @@ int msd_op_attention_trace(const float* q, const float* k, const float* v,
     MSD_TRY(launch_attention(aa, st));
   }
   MSD_TRY(launch_bf16_to_f32(ob, out, static_cast<long long>(nb) * Lq * w, st));
+  MSD_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int msd_op_jax_normal(uint64_t seed, int32_t step, int64_t n, float* out, void* stream) {
+  MSD_REQUIRE(out != nullptr, "msd_op_jax_normal: null argument");
+  uint32_t key[2] = {static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(seed)};
+  if (step >= 0) {
+    uint32_t folded[2];
+    threefry2x32_host(key[0], key[1], 0u, static_cast<uint32_t>(step), folded);
+    key[0] = folded[0];
+    key[1] = folded[1];
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MSD_TRY(launch_jax_normal(key[0], key[1], n, out, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -167,13 +167,19 @@ struct SamplerArgs {
   int ddim;               // 1 = ddim_step, 0 = ddpm_step
   float feat_min, feat_max;
   unsigned long long seed;
+  // rng_kind 1: jax.random threefry stream; keys [num_steps + 1][2] (row 0 PRNGKey(seed), row
+  // i + 1 fold_in(key, i)), device memory
+  int rng_kind;
+  const uint32_t* rng_keys;
 };
 int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream);
 int launch_step_advance(int* step, cudaStream_t stream);
 
 // z0 = init (copy or philox normal), plus its [hi | lo | hi] split.
+// rng_kind / rng_keys as in SamplerArgs (keys row 0 is used)
 int launch_init_z(const float* init_z, float* z, bf16* z_split, long long n, int n_dims,
-                  unsigned long long seed, cudaStream_t stream);
+                  unsigned long long seed, cudaStream_t stream, int rng_kind = 0,
+                  const uint32_t* rng_keys = nullptr);
 
 // x[b,t,:] = E[tok[b,t]] + P[t]
 int launch_embed_tokens(const int* tokens, const float* emb, const float* pos, float* x, int B,
@@ -206,5 +212,7 @@ int launch_sgemm_f32(const float* A, const float* B, float* C, int ldc, int M, i
 int launch_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t stream);
 int launch_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t stream);
 int launch_mask_bits(const int* mask, int nb, int L, uint32_t* bits, cudaStream_t stream);
+// out[0..n) = jax.random.normal(key, [n]) for key = (k0, k1); n a multiple of 8 (test hook)
+int launch_jax_normal(uint32_t k0, uint32_t k1, long long n, float* out, cudaStream_t stream);
 
 }  // namespace msd

@@ -23,8 +23,11 @@ from music_spectrogram_diffusion_b200.config import DiffusionConfig, T5Config
 def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int,
                     targets_length: int, context_length: int, max_batch: int,
                     n_dims: int = 128, feature_min: float = math.log(1e-5),
-                    feature_max: float = 4.0) -> _native.MsdConfig:
-  """Translate the reference's config objects into `struct msd_config`."""
+                    feature_max: float = 4.0, rng: str = 'jax') -> _native.MsdConfig:
+  """Translate the reference's config objects into `struct msd_config`.  rng: 'jax' (the
+  threefry stream of jax.random.PRNGKey(seed), as the reference draws its noise) or 'philox'."""
+  if rng not in ('jax', 'philox'):
+    raise ValueError(f'unknown rng {rng!r}')
   if tuple(t5.mlp_activations) != ('gelu', 'linear'):
     raise NotImplementedError(
         f'mlp_activations={t5.mlp_activations}: only the gated-GELU MLP of the '
@@ -75,7 +78,8 @@ def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int
       train_num_steps=int(tsched.num_steps or 0), logvar_frac=logvar_frac,
       sampler_beta_start=float(sched.start or 0.0), sampler_beta_stop=float(sched.stop or 0.0),
       train_beta_start=float(tsched.start or 0.0), train_beta_stop=float(tsched.stop or 0.0),
-      cross_attend_style=styles[t5.decoder_cross_attend_style])
+      cross_attend_style=styles[t5.decoder_cross_attend_style],
+      rng_kind={'philox': 0, 'jax': 1}[rng])
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
@@ -224,4 +228,12 @@ def op_rmsnorm_film(x: torch.Tensor, gamma: torch.Tensor,
   out = torch.empty_like(x)
   _native.check(lib.msd_op_rmsnorm_film(_ptr(x.contiguous()), _ptr(gamma), _ptr(film), rows, d,
                                         _ptr(out), _stream(x.device)), 'msd_op_rmsnorm_film')
+  return out
+
+
+def op_jax_normal(seed: int, step: int, n: int, device: torch.device) -> torch.Tensor:
+  """Device draw of the jax.random stream (step < 0: init_z; else the noise of scan index step)."""
+  out = torch.empty(n, dtype=torch.float32, device=device)
+  _native.check(_native.load().msd_op_jax_normal(seed, step, n, _ptr(out), _stream(device)),
+                'msd_op_jax_normal')
   return out

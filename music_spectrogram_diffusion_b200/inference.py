@@ -15,9 +15,12 @@ Checkpoints: `checkpoint_path` may be a T5X checkpoint directory such as
 `t5x_checkpoint.py` without t5x/tensorstore), an `.npz` written by `weights.save_npz` (flax
 names, fp32) or `synthetic:<seed>` (random init; no pretrained checkpoint is available offline).
 
-Noise: `seed` feeds the library's Philox generator.  jax.random's threefry stream is a
-third-party detail that cannot be validated offline, so bit-equality with the reference for a
-given seed is NOT claimed; parity runs inject noise through `predict(..., init_z=, noise=)`.
+Noise: with `rng='jax'` (default) `seed` means what it means in the reference -- init_z =
+normal(PRNGKey(seed)), step noise = normal(fold_in(key, i)) -- drawn on the GPU from a restated
+jax.random threefry2x32 stream (`jax_rng.py`: pinned on the Random123 vectors and the values the
+JAX docs print for PRNGKey(0); the fold_in composition is unverified offline).  `rng='philox'`
+selects the library's own Philox4x32-10 stream (restated in oracle/philox.py).  Parity runs can
+also inject noise through `predict(..., init_z=, noise=)`.
 """
 
 from __future__ import annotations
@@ -162,22 +165,26 @@ class InferenceModel:
   """Wrapper of the B200 engine with the reference's `InferenceModel` surface."""
 
   def __init__(self, checkpoint_path: str, gin_config: str, batch_size: int = 1,
-               device: int = 0):
+               device: int = 0, rng: str = 'jax'):
     t5, diff, lengths, codec = _build_from_gin(gin_config)
-    self._init_common(checkpoint_path, t5, diff, lengths, codec, batch_size, device)
+    self._init_common(checkpoint_path, t5, diff, lengths, codec, batch_size, device, rng=rng)
 
   @classmethod
   def from_config(cls, t5: config.T5Config, diffusion: config.DiffusionConfig,
                   sequence_length: Mapping[str, int], checkpoint_path: str = 'synthetic:0',
                   batch_size: int = 1, device: int = 0,
-                  params: Optional[Dict[str, np.ndarray]] = None) -> 'InferenceModel':
+                  params: Optional[Dict[str, np.ndarray]] = None,
+                  rng: str = 'jax') -> 'InferenceModel':
     self = cls.__new__(cls)
     self._init_common(checkpoint_path, t5, diffusion, dict(sequence_length), EventCodecInfo(),
-                      batch_size, device, params)
+                      batch_size, device, params, rng)
     return self
 
   def _init_common(self, checkpoint_path, t5, diff, lengths, codec, batch_size, device,
-                   params=None):
+                   params=None, rng='jax'):
+    if rng not in ('jax', 'philox'):
+      raise ValueError(f'unknown rng {rng!r}')
+    self.rng = rng
     self.checkpoint_path = checkpoint_path
     self.batch_size = batch_size
     self.partitioner = _Partitioner()
@@ -249,7 +256,8 @@ class InferenceModel:
       cfg = engine.make_msd_config(
           self.model.module_config, self.model.diffusion_config, self.inputs_length,
           self.targets_length, self.targets_context_length, self.batch_size,
-          self.audio_codec.n_dims, self.audio_codec.min_value, self.audio_codec.max_value)
+          self.audio_codec.n_dims, self.audio_codec.min_value, self.audio_codec.max_value,
+          rng=self.rng)
       eng = engine.Engine(cfg, self._device_index)
       eng.load_weights(self._restore_from_checkpoint())
       self._params = None  # the engine holds the packed copy

@@ -230,6 +230,48 @@ def test_tail_split_inside_the_step_graph(cuda_device, monkeypatch):
   assert not torch.equal(plain, split)                                   # the split really ran
 
 
+def test_jax_random_stream_on_device_matches_numpy(cuda_device):
+  """rng_kind = 1: the sampler's noise is jax.random.normal of PRNGKey(seed) / fold_in(key, i)
+  (inference.py:203; diffusion_utils.py:389-390, 462).  Device draw vs jax_rng.py (numpy), which
+  tests/test_jax_rng.py pins on the published vectors."""
+  from music_spectrogram_diffusion_b200 import engine, jax_rng as J
+  # the values the JAX docs print for PRNGKey(0), straight from the device generator
+  got = engine.op_jax_normal(0, -1, 8, cuda_device).cpu().numpy()
+  np.testing.assert_allclose(got, J.normal(J.prng_key(0), (8,)), rtol=0, atol=2e-7)
+  for seed, step, n in ((0, -1, 32768), (7, 0, 4096), (123456789, 999, 2 * 256 * 128),
+                        ((5 << 32) | 77, 3, 8)):
+    want = J.init_z(seed, (n,)) if step < 0 else J.step_noise(seed, step, (n,))
+    got = engine.op_jax_normal(seed, step, n, cuda_device).cpu().numpy()
+    # log1p / sqrt differ from numpy by an ulp or two in the tails
+    np.testing.assert_allclose(got, want, rtol=3e-6, atol=3e-7)
+
+
+def test_seeded_sampling_follows_the_jax_stream(cuda_device, tiny):
+  """msd_sample(seed) with rng='jax' == msd_sample with init_z = normal(PRNGKey(seed)) and
+  noise[i] = normal(fold_in(key, i)) injected.  The injected draws come from the device generator
+  (bit-identical inputs -> bit-identical output; an ulp of difference in a normal is amplified
+  22026x by the first reverse step, so numpy-generated draws only agree statistically); the
+  generator itself is checked against numpy in the test above."""
+  from music_spectrogram_diffusion_b200 import engine
+  t5, params = tiny
+  B, steps = 2, 6
+  toks, ctx, cmask = H.make_batch(B, T, C)
+  eng = H.build_engine(t5, T, N, C, B, steps, 2.0, params)
+  assert eng.cfg.rng_kind == 1
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'], b['encoder_continuous_mask'])
+  shape = (B, N, 128)
+  n = B * N * 128
+  for seed in (0, 31337, (9 << 32) | 5):
+    seeded = eng.sample(seed=seed).clone()
+    z0 = engine.op_jax_normal(seed, -1, n, cuda_device).view(shape)
+    noise = torch.stack([engine.op_jax_normal(seed, i, n, cuda_device).view(shape) for i in range(steps)])
+    injected = eng.sample(z0.contiguous(), noise.contiguous()).clone()
+    assert torch.equal(seeded, injected), (seed, (seeded - injected).abs().max().item())
+  assert not torch.equal(eng.sample(seed=1), eng.sample(seed=2))
+  eng.close()
+
+
 def test_sample_internal_rng_is_deterministic(cuda_device, tiny):
   t5, params = tiny
   B, steps = 1, 6
@@ -370,7 +412,8 @@ def test_base_with_context_matches_oracle_fixture(cuda_device, steps):
   diff.classifier_free_guidance.eval_condition_weight = float(g['cond_weight'])
   lengths = dict(config.TASK_FEATURE_LENGTHS_CONTEXT)
   model = inference.InferenceModel.from_config(t5, diff, lengths,
-                                               f'synthetic:{int(g["weight_seed"])}', batch_size=1)
+                                               f'synthetic:{int(g["weight_seed"])}', batch_size=1,
+                                               rng='philox')
   batch = bench.synthetic_batch(1, lengths, seed=int(g['batch_seed']))
   mel, _ = model.predict(batch, seed=int(g['seed']))
   span = 4.0 - np.log(1e-5)

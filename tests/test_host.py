@@ -142,9 +142,10 @@ def test_c_abi_exports_every_declared_symbol(native_lib):
 
 
 def test_struct_layout_matches_header():
-  """msd_config (ABI 2): 17 int32, 4 float, 4 int32, 5 float, 1 int32, no padding; msd_tensor:
+  """msd_config (ABI 2): 17 int32, 4 float, 4 int32, 5 float, 2 int32, no padding; msd_tensor:
   ptr, ptr, int32, int64[4]."""
-  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4 + 4 * 4 + 5 * 4 + 4
+  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4 + 4 * 4 + 5 * 4 + 4 + 4
+  assert _native.MsdConfig.rng_kind.offset == 124
   assert _native.MsdConfig.cross_attend_style.offset == 120
   assert _native.MsdConfig.max_decoder_noise_time.offset == 68
   assert _native.MsdConfig.model_output.offset == 84
