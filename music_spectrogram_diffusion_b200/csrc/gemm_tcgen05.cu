@@ -640,6 +640,7 @@ int gemm_configure() {
   if (int rc = configure_bn<128>()) return rc;
   if (int rc = configure_bn<256>()) return rc;
   if (int rc = configure_pair<64>()) return rc;
+  if (int rc = configure_pair<96>()) return rc;
   if (int rc = configure_pair<128>()) return rc;
   if (int rc = configure_pair<192>()) return rc;
   return configure_pair<256>();
@@ -651,23 +652,17 @@ int gemm_pick_pair_bn(int M, int N) {
   // Measured on B200 (tools/gemm_bench.py): the widest tile wins (least L2->SM traffic per FLOP)
   // unless it leaves clusters idle that a narrower tiling would use: among the widths whose tile
   // count fits the 74 concurrently running clusters, take the one with the most tiles.
+  // (A 96-wide instance exists for the fp32 epilogues, block_n = 96; as a candidate here it
+  // gained nothing, and two overlapped rounds of 96 instead of one of 192 lost 5 %.)
   const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  static const bool small_m_rule = [] {
-    const char* e = getenv("MSD_GEMM_TILE_RULE");  // tuning hook: 0 = only 256 / 192 compete
-    return !(e && e[0] == '0');
-  }();
   const int widths[4] = {256, 192, 128, 64};
   int best = 0, best_tiles = 0;
-  for (int i = 0; i < (small_m_rule ? 4 : 2); ++i) {
+  for (int i = 0; i < 4; ++i) {
     const int bn = widths[i];
     if (N % bn != 0) continue;
     const int tiles = m_pairs * (N / bn);
     if (best == 0) { best = bn; best_tiles = tiles; continue; }   // widest dividing width
     if (best_tiles < 74 && tiles <= 74 && tiles > best_tiles) { best = bn; best_tiles = tiles; }
-  }
-  if (best == 0) {
-    for (int i = 0; i < 4; ++i)
-      if (N % widths[i] == 0) return widths[i];
   }
   return best;
 }
@@ -694,8 +689,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const bool pair = (forced_variant ? forced_variant : a.variant) != 1;
   int bn = a.block_n ? a.block_n
                      : (pair ? gemm_pick_pair_bn(a.M, a.N) : gemm_pick_block_n(a.M, a.N));
-  MSD_REQUIRE(bn == 64 || bn == 128 || bn == 256 || (pair && bn == 192),
-              "gemm: N=%d has no valid tile width", a.N);
+  MSD_REQUIRE(bn == 64 || bn == 128 || bn == 256 || (pair && bn == 192) ||
+                  (pair && bn == 96 && a.epilogue != EPI_BF16 && a.epilogue != EPI_GATED_GELU),
+              "gemm: N=%d has no valid tile width (block_n %d)", a.N, bn);
   MSD_REQUIRE(a.N % bn == 0, "gemm: N=%d not a multiple of block_n=%d", a.N, bn);
   MSD_REQUIRE(a.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", a.ldo);
 
@@ -726,6 +722,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     }
     switch (bn) {
       case 64: return launch_pair<64>(ta, tb, tout, tres, d, stream);
+      case 96: return launch_pair<96>(ta, tb, tout, tres, d, stream);
       case 128: return launch_pair<128>(ta, tb, tout, tres, d, stream);
       case 192: return launch_pair<192>(ta, tb, tout, tres, d, stream);
       default: return launch_pair<256>(ta, tb, tout, tres, d, stream);

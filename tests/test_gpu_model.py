@@ -272,6 +272,28 @@ def test_seeded_sampling_follows_the_jax_stream(cuda_device, tiny):
   eng.close()
 
 
+def test_small_model_one_segment_ten_steps(cuda_device):
+  """BASELINE config 0: small model (gin/models/diffusion/context/t5_small.gin), 1 segment of
+  256 frames x 128 mel bins, 2048 tokens, 10 DDPM steps, against the CPU oracle."""
+  t5 = config.t5_small()
+  Ts, Ns, Cs, steps = 2048, 256, 256, 10
+  params = weights.synthetic_params(t5, Ts, Ns, Cs, seed=1)
+  toks, ctx, cmask = H.make_batch(1, Ts, Cs, seed=4, ctx_masks=[1])
+  toks[0, 1500:] = 0                                 # a realistic, padded token segment
+  init_z, noise = H.make_noise(steps, 1, Ns, seed=6)
+  eng = H.build_engine(t5, Ts, Ns, Cs, 1, steps, 2.0, params)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'], b['encoder_continuous_mask'])
+  mel = eng.sample(init_z.to(cuda_device), noise.to(cuda_device)).cpu()
+  oc = H.oracle_config(t5, steps, 2.0)
+  ref, _ = O.predict_batch_with_aux(O.params_to(params), oc, H.torch_batch(toks, ctx, cmask),
+                                    init_z, noise)
+  err = (mel - ref).abs() / (oc.max_value - oc.min_value) * 2.0
+  assert mel.shape == (1, 256, 128) and torch.isfinite(mel).all()
+  assert err.mean().item() < 3e-2, (err.mean().item(), err.max().item())
+  eng.close()
+
+
 def test_sample_internal_rng_is_deterministic(cuda_device, tiny):
   t5, params = tiny
   B, steps = 1, 6

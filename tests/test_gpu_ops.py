@@ -11,7 +11,7 @@ from tests.helpers import bf16_round
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('variant,block_n', [(0, 0), (0, 64), (0, 128), (0, 192), (0, 256),
+@pytest.mark.parametrize('variant,block_n', [(0, 0), (0, 64), (0, 96), (0, 128), (0, 192), (0, 256),
                                              (1, 0), (1, 64), (1, 128), (1, 256)])
 @pytest.mark.parametrize('M,N,K', [(128, 768, 64), (256, 768, 128), (512, 2304, 768),
                                    (384, 768, 384), (2048 + 128, 1536, 2048)])
