@@ -195,3 +195,27 @@ def test_gin_bindings_reach_the_sampler_variants():
   assert (cfg.logvar_type, cfg.model_output, cfg.sampler_schedule, cfg.train_schedule) == (2, 2, 1, 0)
   assert abs(cfg.logvar_frac - 0.25) < 1e-7 and cfg.num_steps == 250
   assert abs(cfg.sampler_beta_start - 1e-4) < 1e-9 and abs(cfg.sampler_beta_stop - 0.02) < 1e-8
+
+
+REF_GIN = '/root/reference/music_spectrogram_diffusion/gin'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_GIN), reason='reference tree not present on this box')
+def test_every_reference_gin_file_parses():
+  """gin_lite reads the subset of gin the reference's config files use (includes, macros,
+  scoped bindings, configurable references, multi-line values)."""
+  import glob
+  files = sorted(glob.glob(os.path.join(REF_GIN, '**', '*.gin'), recursive=True))
+  assert len(files) >= 25
+  for f in files:
+    gin_lite.parse_config(open(f).read(), ['/root/reference'])
+  sizes = {}
+  for name in ('local_tiny', 't5_small', 't5_base', 't5_large'):
+    g = gin_lite.parse_config(open(os.path.join(REF_GIN, 'models/diffusion/context', name + '.gin')).read(),
+                              ['/root/reference'])
+    b = g.bindings_for('network.T5Config')
+    sizes[name] = (b['emb_dim'], b['num_heads'], b['num_decoder_layers'], b['mlp_dim'])
+  base, small = config.t5_base(), config.t5_small()
+  assert sizes['t5_base'] == (base.emb_dim, base.num_heads, base.num_decoder_layers, base.mlp_dim)
+  assert sizes['t5_small'] == (small.emb_dim, small.num_heads, small.num_decoder_layers, small.mlp_dim)
+  assert sizes['t5_large'] == (1024, 16, 24, 2816)
