@@ -435,3 +435,145 @@ def tokenize_song(notes: np.ndarray, vocab: Optional[EventVocabulary] = None, in
     rows[s, len(ids)] = EOS_ID
     lengths[s] = len(ids) + 1
   return SongTokens(rows, lengths, nframes, frames_per_segment)
+
+
+# ---------------------------------------------------------------------------------------------
+# tokens -> notes (the inverse direction; used for round-trip checks of the tokeniser and by
+# callers that want to look at what a token row says)
+# ---------------------------------------------------------------------------------------------
+DEFAULT_VELOCITY = 100
+DEFAULT_NOTE_DURATION = 0.01
+MIN_NOTE_DURATION = 0.01
+
+
+class NoteDecoder:
+  """Streaming decoder of event ids back into notes (msd/note_sequences.py:264-407 and
+  msd/run_length_encoding.py:274-326; known answers: note_sequences_test.py:289-504).
+
+  Shift tokens give the time since the segment start (consecutive ones add up, any other event
+  re-arms the counter).  With `onsets_only` every pitch token is a note of DEFAULT_NOTE_DURATION;
+  otherwise velocity / program tokens set the state that the following pitch (or drum) tokens
+  use, velocity 0 closing the sounding note of that (pitch, program).  A segment may open with a
+  tie section (`begin_segment`): pitches listed before the 'tie' token stay sounding, every other
+  sounding note is closed at the tie token's time."""
+
+  def __init__(self, vocab: EventVocabulary, onsets_only: bool = False):
+    self.vocab = vocab
+    self.onsets_only = onsets_only
+    self.time = 0.0
+    self.velocity = DEFAULT_VELOCITY
+    self.program = 0
+    self.sounding: Dict[Tuple[int, int], Tuple[float, int]] = {}   # (pitch, program) -> (onset, vel)
+    self.tied: set = set()
+    self.in_tie_section = False
+    self.rows: List[Tuple[float, float, int, int, int, bool]] = []
+
+  # -- helpers -------------------------------------------------------------------------------
+  def _emit(self, start: float, end: float, pitch: int, velocity: int, program: int = 0,
+            is_drum: bool = False) -> None:
+    self.rows.append((start, max(end, start + MIN_NOTE_DURATION), pitch, velocity, program, is_drum))
+
+  def _close(self, key: Tuple[int, int], end: float) -> None:
+    onset, velocity = self.sounding.pop(key)
+    self._emit(onset, end, key[0], velocity, key[1])
+
+  def begin_segment(self) -> None:
+    self.tied = set()
+    self.in_tie_section = True
+
+  # -- one event -----------------------------------------------------------------------------
+  def _event(self, time: float, kind: str, value: int) -> None:
+    if self.onsets_only:
+      if kind != 'pitch':
+        raise ValueError(f'unexpected event type: {kind}')
+      self._emit(time, time + DEFAULT_NOTE_DURATION, value, DEFAULT_VELOCITY)
+      return
+    if time < self.time:
+      raise ValueError(f'event time < current time, {time} < {self.time}')
+    self.time = time
+    key = (value, self.program)
+    if kind == 'pitch':
+      if self.in_tie_section:
+        if key not in self.sounding:
+          raise ValueError(f'inactive pitch/program in tie section: {value}/{self.program}')
+        if key in self.tied:
+          raise ValueError(f'pitch/program is already tied: {value}/{self.program}')
+        self.tied.add(key)
+      elif self.velocity == 0:
+        if key not in self.sounding:
+          raise ValueError(f'note-off for inactive pitch/program: {value}/{self.program}')
+        self._close(key, time)
+      else:
+        if key in self.sounding:        # re-struck without a note-off: end the earlier note here
+          self._close(key, time)
+        self.sounding[key] = (time, self.velocity)
+    elif kind == 'drum':
+      if self.velocity == 0:
+        raise ValueError('velocity cannot be zero for drum event')
+      self._emit(time, time + DEFAULT_NOTE_DURATION, value, self.velocity, 0, True)
+    elif kind == 'velocity':
+      self.velocity = bin_to_velocity(value, num_velocity_bins_of(self.vocab))
+    elif kind == 'program':
+      self.program = value
+    elif kind == 'tie':
+      if not self.in_tie_section:
+        raise ValueError('tie section end event when not in tie section')
+      for k in [k for k in self.sounding if k not in self.tied]:
+        self._close(k, self.time)
+      self.in_tie_section = False
+    else:
+      raise ValueError(f'unexpected event type: {kind}')
+
+  # -- a run of event ids ------------------------------------------------------------------------
+  def feed(self, event_ids: Sequence[int], start_time: float = 0.0,
+           max_time: Optional[float] = None) -> Tuple[int, int]:
+    """Returns (ids that could not be decoded or applied, ids dropped beyond max_time)."""
+    invalid = dropped = 0
+    steps = 0
+    now = start_time
+    event_ids = list(event_ids)
+    for i, tok in enumerate(event_ids):
+      try:
+        kind, value = self.vocab.decode(int(tok))
+      except ValueError:
+        invalid += 1
+        continue
+      if kind == 'shift':
+        steps += value
+        now = start_time + steps / self.vocab.steps_per_second
+        if max_time and now > max_time:
+          dropped = len(event_ids) - i
+          break
+        continue
+      steps = 0
+      try:
+        self._event(now, kind, value)
+      except ValueError:
+        invalid += 1
+    return invalid, dropped
+
+  def finish(self) -> np.ndarray:
+    """Closes whatever still sounds (at the latest time seen, at least MIN_NOTE_DURATION after its
+    onset) and returns the notes."""
+    for onset, _ in self.sounding.values():
+      self.time = max(self.time, onset + MIN_NOTE_DURATION)
+    for k in list(self.sounding):
+      self._close(k, self.time)
+    return make_notes(self.rows)
+
+
+def decode_song(tokens: np.ndarray, vocab: EventVocabulary, frames_per_segment: int = 256,
+                frame_rate: int = 50, include_ties: bool = True) -> Tuple[np.ndarray, int, int]:
+  """Rows of model ids as produced by `tokenize_song` -> (notes, invalid ids, dropped ids)."""
+  dec = NoteDecoder(vocab)
+  invalid = dropped = 0
+  seconds = frames_per_segment / frame_rate
+  for s, row in enumerate(np.asarray(tokens)):
+    ids = from_model_ids(row, vocab.num_classes)
+    ids = ids[ids >= 0]                                    # strip EOS marker and padding
+    if include_ties:
+      dec.begin_segment()
+    a, b = dec.feed(ids, start_time=s * seconds, max_time=None)
+    invalid += a
+    dropped += b
+  return dec.finish(), invalid, dropped

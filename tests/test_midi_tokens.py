@@ -246,3 +246,67 @@ def test_tokenize_song_segments_ties_and_limits():
   with pytest.raises(ValueError, match='exceeds maximum length'):
     M.tokenize_song(dense, v)
   assert M.tokenize_song(M.make_notes([]), v).tokens.shape == (1, 2048)
+
+
+# ---- tokens -> notes: known answers of note_sequences_test.py:289-504 ------------------------
+def _decode(events, onsets_only, start=0.0, max_time=None):
+  d = M.NoteDecoder(TEST_VOCAB, onsets_only=onsets_only)
+  invalid, dropped = d.feed(events, start_time=start, max_time=max_time)
+  notes = d.finish()
+  rows = [(round(float(n['start']), 6), round(float(n['end']), 6), int(n['pitch']), int(n['velocity']),
+           int(n['program']), bool(n['is_drum'])) for n in notes]
+  return rows, invalid, dropped
+
+
+def test_decode_known_answers():
+  assert _decode([25, 161, 50, 162], True) == (
+      [(0.25, 0.26, 60, 100, 0, False), (0.50, 0.51, 61, 100, 0, False)], 0, 0)
+  assert _decode([5, 161, 25, 162], True) == (
+      [(0.05, 0.06, 60, 100, 0, False), (0.25, 0.26, 61, 100, 0, False)], 0, 0)
+  assert _decode([5, 356, 161, 25, 229, 161], False) == ([(0.05, 0.25, 60, 127, 0, False)], 0, 0)
+  # a second onset without a note-off ends the first note where the second begins
+  assert _decode([5, 356, 161, 10, 161, 25, 229, 161], False) == (
+      [(0.05, 0.10, 60, 127, 0, False), (0.10, 0.25, 60, 127, 0, False)], 0, 0)
+  rows, invalid, dropped = _decode([5, 525, 356, 161, 15, 356, 394, 25, 525, 229, 161], False)
+  assert (invalid, dropped) == (0, 0)
+  assert sorted(rows) == [(0.05, 0.25, 60, 127, 40, False), (0.15, 0.16, 37, 127, 0, True)]
+
+
+def test_decode_invalid_and_dropped_events():
+  assert _decode([5, -1, 161, -2, 25, 162, 9999], True) == (
+      [(0.05, 0.06, 60, 100, 0, False), (0.25, 0.26, 61, 100, 0, False)], 3, 0)
+  assert _decode([161, 25, 162], True, start=1.0, max_time=1.25) == (
+      [(1.00, 1.01, 60, 100, 0, False), (1.25, 1.26, 61, 100, 0, False)], 0, 0)
+  assert _decode([5, 161, 30, 162], True, start=1.0, max_time=1.25) == (
+      [(1.05, 1.06, 60, 100, 0, False)], 0, 2)
+  assert _decode([25, 230, 50, 161], True) == ([(0.50, 0.51, 60, 100, 0, False)], 1, 0)
+
+
+@pytest.mark.parametrize('seed', range(5))
+def test_tokenize_decode_round_trip(seed):
+  """notes -> per-segment token rows -> notes gives back the song on the 10 ms grid."""
+  rng = np.random.default_rng(100 + seed)
+  rows, cursor = [], {}
+  for _ in range(int(rng.integers(5, 80))):
+    prog = int(rng.choice([0, 24, 40, 73]))
+    pitch = int(rng.integers(40, 90))
+    t0 = max(cursor.get((prog, pitch), 0.0), float(rng.uniform(0, 14))) + 0.02
+    t0 = round(t0, 2)
+    t1 = round(t0 + float(rng.uniform(0.03, 3.0)), 2)
+    cursor[(prog, pitch)] = t1                       # no overlapping notes on one (program, pitch)
+    rows.append((t0, t1, pitch, int(rng.integers(1, 128)), prog, False))
+  for _ in range(int(rng.integers(0, 10))):
+    t0 = round(float(rng.uniform(0, 14)), 2)
+    rows.append((t0, t0 + 0.01, int(rng.integers(35, 50)), int(rng.integers(1, 128)), 0, True))
+  notes = M.make_notes(rows)
+  vocab = M.mt3_event_vocabulary()
+  song = M.tokenize_song(notes, vocab, map_to_slakh_programs=False)
+  back, invalid, dropped = M.decode_song(song.tokens, vocab)
+  assert (invalid, dropped) == (0, 0) and len(back) == len(notes)
+  key = lambda a: np.lexsort((a['pitch'], a['program'], a['is_drum'], np.round(a['start'], 2)))
+  a, b = notes[key(notes)], back[key(back)]
+  np.testing.assert_allclose(b['start'], a['start'], atol=1e-9)
+  pitched = ~a['is_drum']
+  np.testing.assert_allclose(b['end'][pitched], a['end'][pitched], atol=1e-9)
+  for f in ('pitch', 'velocity', 'program', 'is_drum'):
+    np.testing.assert_array_equal(a[f], b[f])
