@@ -310,3 +310,41 @@ def test_tokenize_decode_round_trip(seed):
   np.testing.assert_allclose(b['end'][pitched], a['end'][pitched], atol=1e-9)
   for f in ('pitch', 'velocity', 'program', 'is_drum'):
     np.testing.assert_array_equal(a[f], b[f])
+
+
+def test_run_length_encoding_preserves_event_times_property():
+  """For any stream of single-step shifts and events: every kept event keeps its time since the
+  segment start, runs never exceed max_shift_steps, and no trailing shift survives."""
+  hypothesis = pytest.importorskip('hypothesis')
+  from hypothesis import given, settings, strategies as st
+  vocab = TEST_VOCAB
+  shift1 = vocab.encode('shift', 1)
+  lo, hi = vocab.id_range('pitch')
+
+  @settings(max_examples=200, deadline=None)
+  @given(st.lists(st.one_of(st.just(shift1), st.integers(lo, hi)), max_size=400))
+  def check(stream):
+    out = M.run_length_encode_shifts(stream, vocab)
+    # times of the non-shift events in the input
+    t, want = 0, []
+    for tok in stream:
+      if tok == shift1:
+        t += 1
+      else:
+        want.append((t, tok))
+    # times of the events in the output (absolute runs, re-armed by every event)
+    got, run = [], 0
+    last_time = 0
+    for tok in out:
+      if vocab.is_shift(int(tok)):
+        assert 1 <= tok <= vocab.max_shift_steps
+        run += int(tok)
+      else:
+        if run:
+          last_time = run
+        got.append((last_time, int(tok)))
+        run = 0
+    assert got == want
+    assert not len(out) or not vocab.is_shift(int(out[-1]))
+
+  check()
