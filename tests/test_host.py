@@ -219,3 +219,28 @@ def test_every_reference_gin_file_parses():
   assert sizes['t5_base'] == (base.emb_dim, base.num_heads, base.num_decoder_layers, base.mlp_dim)
   assert sizes['t5_small'] == (small.emb_dim, small.num_heads, small.num_decoder_layers, small.mlp_dim)
   assert sizes['t5_large'] == (1024, 16, 24, 2816)
+
+
+def test_header_is_plain_c(tmp_path):
+  """include/msd_b200.h is the C ABI: it must compile as C99 and as C++ without any other header
+  of this repository, and a C caller must see the struct layout the ctypes binding uses."""
+  import shutil
+  import subprocess
+  if not shutil.which('gcc'):
+    pytest.skip('no gcc')
+  hdr = os.path.join(ROOT, 'include', 'msd_b200.h')
+  for cmd in (['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-fsyntax-only', '-x', 'c', hdr],
+              ['g++', '-std=c++17', '-fsyntax-only', '-x', 'c++', hdr]):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+  src = tmp_path / 'layout.c'
+  src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "msd_b200.h"\n'
+                 'int main(void) { printf("%zu %zu %zu %zu %d\\n", sizeof(msd_config), '
+                 'offsetof(msd_config, rng_kind), sizeof(msd_tensor), offsetof(msd_tensor, shape), '
+                 'MSD_B200_ABI_VERSION); return 0; }\n')
+  exe = tmp_path / 'layout'
+  subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
+                 check=True)
+  out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+  assert [int(x) for x in out] == [ctypes.sizeof(_native.MsdConfig), _native.MsdConfig.rng_kind.offset,
+                                   ctypes.sizeof(_native.MsdTensor), _native.MsdTensor.shape.offset, 2]
