@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MSD_B200_ABI_VERSION 2
+#define MSD_B200_ABI_VERSION 3
 
 typedef struct msd_ctx msd_ctx;
 
@@ -69,6 +69,13 @@ typedef struct msd_config {
                                     (library stream), 1 = jax.random threefry2x32 stream of
                                     PRNGKey(seed) / fold_in(key, i) (inference.py:203,
                                     diffusion_utils.py:389-390, 462) */
+  /* ABI 3 */
+  int32_t precision;             /* T5Config.dtype as executed: 0 = bf16 tensor-core operands with
+                                    fp32 accumulation / residual / softmax (the fast path);
+                                    1 = fp32-accurate: every dense layer as a 3 x bf16 split-
+                                    precision tensor-core product (~2^-16 per product), fp32
+                                    attention, exact tanh -- what the shipped gins ask for
+                                    (gin/models/diffusion/context/t5_base.gin:72 dtype float32) */
 } msd_config;
 
 /* A named fp32 parameter in the reference's own layout (flax tree path joined by '/',
@@ -171,6 +178,29 @@ int msd_op_attention_trace(const float* q, const float* k, const float* v,
                            const int32_t* key_mask, int32_t nb, int32_t heads, int32_t Lq,
                            int32_t Lk, float* out, int64_t* trace, void* stream);
 
+/* DenseGeneral with each fused epilogue of the hot path (kernels.h GemmEpilogue), for unit parity:
+ *   0 bf16 out                      out [M, N]            = bf16(a w)
+ *   2 f32 + residual                out [M, N]            = a w + resid [M, N]
+ *   3 gated GELU (layers.py:483-509) out [M, N]           = bf16(gelu_tanh(a w) * (a w1)), w / w1 [K, N]
+ *   4 f32 + position rows           out [M (+ dup), N]    = a w + pos[(r % pos_rows - shift[r /
+ *                                    pos_rows]) mod pos_rows] (network.py:327-334, 420-427), rows
+ *                                    also stored at r + dup_rows when dup_rows > 0
+ *   5 gated GELU, fp32-accurate     out [M, N]            = hi + lo of the [hi | lo | hi] output,
+ *                                    computed from 3 x bf16 split operands (a, w, w1 used in full
+ *                                    fp32 precision)
+ * a [M, K], w [K, N] f32 device (bf16-rounded by the caller for epilogues 0-4); block_n 0 = auto.
+ * Unused pointers may be NULL.  out is f32 device. */
+int msd_op_dense_epilogue(const float* a, const float* w, const float* w1, int32_t M, int32_t N,
+                          int32_t K, int32_t epilogue, int32_t block_n, const float* resid,
+                          const float* pos, int32_t pos_rows, const int32_t* pos_shift,
+                          int32_t dup_rows, float* out, void* stream);
+
+/* dot_product_attention of the fp32-accurate mode: as msd_op_attention, but q / k / v are used in
+ * full fp32 and the result is returned as hi + lo of the kernel's [hi | lo | hi] output. */
+int msd_op_attention_f32(const float* q, const float* k, const float* v, const int32_t* key_mask,
+                         int32_t nb, int32_t heads, int32_t Lq, int32_t Lk, float* out,
+                         void* stream);
+
 /* LayerNorm (layers.py:632-649) followed by optional FiLM (layers.py:652-666) with explicit
  * scale|bias vector film [2*d] (NULL = none): out f32 (bf16-rounded) [rows, d]. */
 int msd_op_rmsnorm_film(const float* x, const float* gamma, const float* film, int32_t rows,
@@ -180,6 +210,10 @@ int msd_op_rmsnorm_film(const float* x, const float* gamma, const float* film, i
  * diffusion_utils.py:462), else normal(fold_in(PRNGKey(seed), step), [n]) (389-390).
  * out: device f32 [n], n a multiple of 8.  Test hook for the rng_kind = 1 generator. */
 int msd_op_jax_normal(uint64_t seed, int32_t step, int64_t n, float* out, void* stream);
+
+/* The raw threefry2x32 words those normals are made from (jax.random.bits of the same key):
+ * out device uint32 [n].  Integer work: the test compares bit-exactly. */
+int msd_op_jax_bits(uint64_t seed, int32_t step, int64_t n, uint32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

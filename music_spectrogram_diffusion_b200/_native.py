@@ -18,7 +18,8 @@ _CSRC = os.path.join(_HERE, 'csrc')
 _INCLUDE = os.path.join(os.path.dirname(_HERE), 'include')
 LIB_NAME = 'libmsd_b200.so'
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
-SOURCES = ['gemm_tcgen05.cu', 'attention_tcgen05.cu', 'elementwise.cu', 'engine.cu']
+SOURCES = ['gemm_tcgen05.cu', 'attention_tcgen05.cu', 'attention_f32.cu', 'elementwise.cu',
+           'engine.cu']
 HEADERS = ['common.cuh', 'kernels.h']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
@@ -92,7 +93,7 @@ class MsdConfig(ctypes.Structure):
       ('logvar_frac', ctypes.c_float), ('sampler_beta_start', ctypes.c_float),
       ('sampler_beta_stop', ctypes.c_float), ('train_beta_start', ctypes.c_float),
       ('train_beta_stop', ctypes.c_float), ('cross_attend_style', ctypes.c_int32),
-      ('rng_kind', ctypes.c_int32),
+      ('rng_kind', ctypes.c_int32), ('precision', ctypes.c_int32),
   ]
 
 
@@ -127,7 +128,11 @@ SYMBOLS = [
     ('msd_op_attention_trace', ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     ('msd_op_rmsnorm_film', ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P]),
     ('msd_op_jax_normal', ctypes.c_int, [ctypes.c_uint64, _I, ctypes.c_int64, _P, _P]),
+    ('msd_op_jax_bits', ctypes.c_int, [ctypes.c_uint64, _I, ctypes.c_int64, _P, _P]),
+    ('msd_op_dense_epilogue', ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P]),
+    ('msd_op_attention_f32', ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
 ]
+ABI_VERSION = 3  # MSD_B200_ABI_VERSION of include/msd_b200.h this binding was written against
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -147,6 +152,10 @@ def load() -> ctypes.CDLL:
     fn = getattr(lib, name)  # AttributeError if the symbol is not exported
     fn.restype = restype
     fn.argtypes = argtypes
+  got = lib.msd_abi_version()
+  if got != ABI_VERSION:
+    raise MsdError(f'{LIB_PATH} implements ABI {got}, this binding expects {ABI_VERSION}: the '
+                   'shared object is stale, rebuild it (python -c "import __graft_entry__ as g; g.build()")')
   _lib = lib
   return lib
 

@@ -9,7 +9,7 @@
 
 namespace msd {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 namespace {
 
@@ -208,32 +208,35 @@ __device__ __forceinline__ float jax_normal_from_bits(uint32_t bits) {
   return 1.41421354f * erfinv_xla(u);
 }
 
-// normals for elements [4*i4, 4*i4 + 4) of an n-element draw (n a multiple of 8)
-__device__ __forceinline__ float4 jax_normal4(const uint32_t* key, long long n, long long i4) {
+// random words for elements [4*i4, 4*i4 + 4) of an n-element draw (n a multiple of 8)
+__device__ __forceinline__ uint4 jax_bits4(const uint32_t* key, long long n, long long i4) {
   const uint32_t k0 = key[0], k1 = key[1];
   const long long half = n >> 1, e = i4 * 4;
-  float r[4];
+  uint32_t r[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const long long ej = e + j;
     const bool second = ej >= half;
     const uint32_t c0 = static_cast<uint32_t>(second ? ej - half : ej);
     const uint2 o = threefry2x32(k0, k1, c0, static_cast<uint32_t>(c0 + half));
-    r[j] = jax_normal_from_bits(second ? o.y : o.x);
+    r[j] = second ? o.y : o.x;
   }
-  return make_float4(r[0], r[1], r[2], r[3]);
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+// normals for the same elements
+__device__ __forceinline__ float4 jax_normal4(const uint32_t* key, long long n, long long i4) {
+  const uint4 b = jax_bits4(key, n, i4);
+  return make_float4(jax_normal_from_bits(b.x), jax_normal_from_bits(b.y),
+                     jax_normal_from_bits(b.z), jax_normal_from_bits(b.w));
 }
 
 // ---------------------------------------------------------------------------
 // One reverse-diffusion update (CFG combine + x0 + clip + DDPM/DDIM mean + noise)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) {
-  griddep_launch_dependents();
-  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void sampler_step_body(const SamplerArgs& a, int step,
+                                                  const float* noise_base, float* mel_base,
+                                                  unsigned long long seed, long long i4) {
   const long long idx = i4 * 4;
-  if (idx >= a.n) return;
-  griddep_wait();
-  const int step = *a.step;
   const float* cf = a.coef + static_cast<size_t>(step) * MSD_STEP_COLS;
   const float x0_scale = cf[0], eps_scale = cf[1], c_z = cf[2], c_x0 = cf[3], sigma = cf[4];
   const bool last = cf[5] != 0.f;
@@ -287,12 +290,12 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) 
   } else {
     float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sigma != 0.f) {
-      if (a.noise != nullptr) {
-        nz = *reinterpret_cast<const float4*>(a.noise + static_cast<size_t>(step) * a.n + idx);
+      if (noise_base != nullptr) {
+        nz = *reinterpret_cast<const float4*>(noise_base + static_cast<size_t>(step) * a.n + idx);
       } else {
         nz = a.rng_kind == 1
                  ? jax_normal4(a.rng_keys + 2 * (step + 1), a.n, i4)
-                 : philox_normal4(a.seed, static_cast<uint32_t>(step) + 1u,
+                 : philox_normal4(seed, static_cast<uint32_t>(step) + 1u,
                                   static_cast<unsigned long long>(i4));
       }
     }
@@ -301,20 +304,46 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) 
   }
   *reinterpret_cast<float4*>(a.z + idx) = zn;
   store_split4(a.z_split, idx, a.n_dims, zn);
-  if (last && a.mel_out != nullptr) {
+  if (last && mel_base != nullptr) {
     // scale_to_features, msd/audio_codecs.py:176-183 with input_range (-1, 1)
     const float span = a.feat_max - a.feat_min;
     float4 f;
     f.x = (zn.x + 1.f) * 0.5f * span + a.feat_min; f.y = (zn.y + 1.f) * 0.5f * span + a.feat_min;
     f.z = (zn.z + 1.f) * 0.5f * span + a.feat_min; f.w = (zn.w + 1.f) * 0.5f * span + a.feat_min;
-    *reinterpret_cast<float4*>(a.mel_out + idx) = f;
+    *reinterpret_cast<float4*>(mel_base + idx) = f;
   }
 }
 
-__global__ void step_advance_kernel(int* step) {
+__global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) {
   griddep_launch_dependents();
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   griddep_wait();
-  *step -= 1;
+  if (a.run == nullptr) {
+    if (i4 * 4 < a.n) sampler_step_body(a, *a.step, a.noise, a.mel_out, a.seed, i4);
+    return;
+  }
+  // Per-call arguments and the step index live in device memory (RunArgs).  The step advance is
+  // folded in: every block counts itself done once all its threads hold `step` in a register, and
+  // the last one to arrive decrements it for the next graph launch.
+  __shared__ int s_step;
+  if (threadIdx.x == 0) {
+    // thread 0 alone reads the step index (its store to shared memory needs the loaded value, so
+    // the load has completed before the atomic below is issued) and hands it to the block
+    const int st = *reinterpret_cast<volatile int*>(&a.run->step);
+    s_step = st;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&a.run->done, 1u);
+    if (prev == gridDim.x - 1) {
+      a.run->done = 0u;
+      a.run->step = st - 1;
+    }
+  }
+  __syncthreads();
+  const int step = s_step;
+  const float* noise_base = a.run->noise;
+  float* mel_base = a.run->mel_out;
+  const unsigned long long seed = a.run->seed;
+  if (i4 * 4 < a.n) sampler_step_body(a, step, noise_base, mel_base, seed, i4);
 }
 
 __global__ void __launch_bounds__(256)
@@ -363,6 +392,15 @@ scale_split_kernel(const float* feat, bf16* out, long long n, int n_dims, float 
   f.z = (fminf(fmaxf(f.z, fmin), fmax) - fmin) * inv * 2.0f - 1.0f;
   f.w = (fminf(fmaxf(f.w, fmin), fmax) - fmin) * inv * 2.0f - 1.0f;
   store_split4(out, idx, n_dims, f);
+}
+
+// rows of fp32 -> [hi | lo | hi] bf16 rows (A operand of a split-precision GEMM)
+__global__ void __launch_bounds__(256)
+split3_rows_kernel(const float* src, bf16* out, long long n, int cols) {
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long idx = i4 * 4;
+  if (idx >= n) return;
+  store_split4(out, idx, cols, *reinterpret_cast<const float4*>(src + idx));
 }
 
 // One block per batch row: key-mask bit words for [tokens | context] and the
@@ -414,14 +452,17 @@ pack_weight_kernel(const float* W, int K, int N, bf16* dst, int ldd, int n_off, 
 }
 
 __global__ void __launch_bounds__(256)
-pack_gated_kernel(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd) {
+pack_gated_kernel(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd, int k_off,
+                  int part) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= 2LL * F * K) return;
   const int r = static_cast<int>(gid / K), k = static_cast<int>(gid - static_cast<long long>(r) * K);
   const int g = r >> 6, j = r & 63;
   const float* W = (j < 32) ? W0 : W1;
   const int col = g * 32 + (j & 31);
-  dst[static_cast<size_t>(r) * ldd + k] = __float2bfloat16_rn(W[static_cast<size_t>(k) * F + col]);
+  bf16 hi, lo;
+  split_bf16(W[static_cast<size_t>(k) * F + col], hi, lo);
+  dst[static_cast<size_t>(r) * ldd + k_off + k] = part ? lo : hi;
 }
 
 constexpr int SG_T = 64, SG_K = 16;
@@ -478,6 +519,17 @@ __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16* s, float* 
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) d[i] = __bfloat162float(s[i]);
 }
+// dst[r][c] = src[r * ld + c] (+ src[r * ld + lo_off + c] when lo_off > 0: hi + lo of a split row)
+__global__ void __launch_bounds__(256)
+bf16_rows_to_f32_kernel(const bf16* s, int ld, int lo_off, float* d, long long rows, int cols) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = static_cast<int>(i - r * cols);
+  float v = __bfloat162float(s[r * ld + c]);
+  if (lo_off > 0) v += __bfloat162float(s[r * ld + lo_off + c]);
+  d[i] = v;
+}
 __global__ void __launch_bounds__(256)
 mask_bits_kernel(const int* mask, long long words, uint32_t* bits) {
   const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -501,8 +553,6 @@ int elementwise_configure() {
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   MSD_CUDA_CHECK(cudaFuncSetAttribute(sampler_step_kernel,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  MSD_CUDA_CHECK(cudaFuncSetAttribute(step_advance_kernel,
-                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   MSD_CUDA_CHECK(cudaFuncSetAttribute(init_z_kernel,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   return 0;
@@ -524,12 +574,13 @@ int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* ou
 }
 
 int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src_len, int d,
-                              bf16* out, int dst_len, int dst_off, cudaStream_t stream) {
+                              bf16* out, int dst_len, int dst_off, cudaStream_t stream,
+                              int split3) {
   MSD_REQUIRE(d % 128 == 0 && d <= 128 * NORM_MAX_ITERS, "rmsnorm: d=%d must be k*128 <= 1024", d);
   NormDev p;
   p.x = x; p.gamma = gamma; p.out = out; p.film = nullptr; p.step = nullptr;
   p.film_step_stride = 0; p.film_offset = 0;
-  p.rows = B * src_len; p.d = d; p.ldo = d; p.split3 = 0;
+  p.rows = B * src_len; p.d = d; p.ldo = split3 ? 3 * d : d; p.split3 = split3;
   p.src_len = src_len; p.dst_len = dst_len; p.dst_off = dst_off;
   MSD_CUDA_CHECK(launch_kernel(rmsnorm_film_kernel, dim3(blocks_for(p.rows, 8)), dim3(256), 0, stream, p));
   ++g_launch_count;
@@ -544,19 +595,27 @@ int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream) {
   return 0;
 }
 
-int launch_step_advance(int* step, cudaStream_t stream) {
-  ProfScope prof(KC_OTHER, 0.0, 8.0, stream);
-  MSD_CUDA_CHECK(launch_kernel(step_advance_kernel, dim3(1), dim3(1), 0, stream, step));
-  ++g_launch_count;
-  return 0;
-}
-
 __global__ void __launch_bounds__(256)
 jax_normal_kernel(uint32_t k0, uint32_t k1, long long n, float* out) {
   const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
   const uint32_t key[2] = {k0, k1};
   *reinterpret_cast<float4*>(out + i4 * 4) = jax_normal4(key, n, i4);
+}
+
+__global__ void __launch_bounds__(256)
+jax_bits_kernel(uint32_t k0, uint32_t k1, long long n, uint32_t* out) {
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  const uint32_t key[2] = {k0, k1};
+  *reinterpret_cast<uint4*>(out + i4 * 4) = jax_bits4(key, n, i4);
+}
+
+int launch_jax_bits(uint32_t k0, uint32_t k1, long long n, uint32_t* out, cudaStream_t stream) {
+  MSD_REQUIRE(n > 0 && n % 8 == 0 && n < (1ll << 32), "jax_bits: n must be k*8 < 2^32");
+  jax_bits_kernel<<<blocks_for(n / 4, 256), 256, 0, stream>>>(k0, k1, n, out);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 int launch_jax_normal(uint32_t k0, uint32_t k1, long long n, float* out, cudaStream_t stream) {
@@ -598,6 +657,15 @@ int launch_scale_split(const float* feat, bf16* out_split, long long rows, int n
   return 0;
 }
 
+int launch_split3_rows(const float* src, bf16* out_split, long long rows, int cols,
+                       cudaStream_t stream) {
+  MSD_REQUIRE(cols % 4 == 0, "split3_rows: cols must be a multiple of 4");
+  const long long n = rows * cols;
+  split3_rows_kernel<<<blocks_for(n / 4, 256), 256, 0, stream>>>(src, out_split, n, cols);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int launch_build_masks(const int* tokens, const int* ctx_mask, int B, int T, int C, uint32_t* bits,
                        int* ctx_seq_len, int terminal_relative, cudaStream_t stream) {
   MSD_REQUIRE(T % 128 == 0 && C % 128 == 0, "masks: lengths must be multiples of 128");
@@ -617,9 +685,10 @@ int launch_pack_weight(const float* W, int K, int N, bf16* dst, int ldd, int n_o
 }
 
 int launch_pack_gated(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int k_off, int part) {
   MSD_REQUIRE(F % 32 == 0, "pack_gated: F must be a multiple of 32");
-  pack_gated_kernel<<<blocks_for(2LL * F * K, 256), 256, 0, stream>>>(W0, W1, K, F, dst, ldd);
+  pack_gated_kernel<<<blocks_for(2LL * F * K, 256), 256, 0, stream>>>(W0, W1, K, F, dst, ldd, k_off,
+                                                                      part);
   MSD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -631,6 +700,13 @@ int launch_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t st
 }
 int launch_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t stream) {
   bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(src, dst, n);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_bf16_rows_to_f32(const bf16* src, int ld, int lo_off, float* dst, long long rows, int cols,
+                            cudaStream_t stream) {
+  bf16_rows_to_f32_kernel<<<blocks_for(rows * cols, 256), 256, 0, stream>>>(src, ld, lo_off, dst,
+                                                                            rows, cols);
   MSD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -24,6 +24,16 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
+__host__ __device__ inline bool epi_is_bf16_out(int e) {
+  return e == EPI_BF16 || e == EPI_GATED_GELU || e == EPI_GATED_GELU_SPLIT3;
+}
+
+// exact-tanh GELU of the fp32-accurate mode (flax.linen.gelu(approximate=True))
+__device__ __forceinline__ float gelu_tanh_exact(float x) {
+  const float k0 = 0.7978845608028654f;
+  return 0.5f * x * (1.0f + tanhf(k0 * (x + 0.044715f * x * x * x)));
+}
+
 struct GemmDev {
   int M, N, K;
   int epilogue;
@@ -369,7 +379,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     fence_barrier_init();
   }
-  if (warp == 2 && lane == 0 && p.epilogue != EPI_BF16 && p.epilogue != EPI_GATED_GELU) {
+  if (warp == 2 && lane == 0 && !epi_is_bf16_out(p.epilogue)) {
     tma_prefetch_desc(&tmap_out);
     if (p.epilogue == EPI_RESID_F32) tma_prefetch_desc(&tmap_res);
   }
@@ -444,7 +454,6 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint8_t* tile_smem = sEpi + lg * 4096;
     uint8_t* sO = sEpi;               // [2][16 KB]
     uint8_t* sR = sEpi + 2 * 16384;   // [2][16 KB]
-    const bool f32_path = p.epilogue != EPI_BF16 && p.epilogue != EPI_GATED_GELU;
     const bool has_res = p.epilogue == EPI_RESID_F32;
     const bool epi_leader = (warp == 2 && lane == 0);
     constexpr int NCH = BN / 32;
@@ -488,6 +497,34 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                pack_bf16(v[6], v[7]));
           }
           epilogue_bf16_rows<4>(p, tile_smem, lane, row0, (n0 + c) / 2, ch);
+        }
+      } else if (p.epilogue == EPI_GATED_GELU_SPLIT3) {
+        // fp32-accurate mode: exact tanh, result kept to ~16 mantissa bits as [hi | lo | hi]
+        uint32_t g[32];
+        const int F = p.N / 2;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          tmem_ld_32x32b_x32(t_row + c, r);
+          tmem_ld_32x32b_x32(t_row + c + 32, g);
+          tmem_ld_wait();
+          uint4 chh[4], chl[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[i] = gelu_tanh_exact(__uint_as_float(r[8 * q + i])) * __uint_as_float(g[8 * q + i]);
+              lo[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+            }
+            chh[q] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                pack_bf16(v[6], v[7]));
+            chl[q] = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]),
+                                pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+          }
+          const int oc = (n0 + c) / 2;
+          epilogue_bf16_rows<4>(p, tile_smem, lane, row0, oc, chh);
+          epilogue_bf16_rows<4>(p, tile_smem, lane, row0, F + oc, chl);
+          epilogue_bf16_rows<4>(p, tile_smem, lane, row0, 2 * F + oc, chh);
         }
       } else if (p.epilogue == EPI_BF16) {
         uint32_t g[32];
@@ -587,13 +624,27 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+// SMs of the current device (148 on B200): the persistent grid is one CTA pair per two SMs.
+static int gemm_sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
 template <int BN>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                 const CUtensorMap& tres, const GemmDev& d, cudaStream_t st) {
   using Cfg = PairCfg<BN>;
   const int m_pairs = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_tiles = m_pairs * (d.N / BN);
-  int sms = 148;
+  const int sms = gemm_sm_count();
   const int clusters = num_tiles < sms / 2 ? num_tiles : sms / 2;
   ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
                  2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
@@ -656,13 +707,14 @@ int gemm_pick_pair_bn(int M, int N) {
   // gained nothing, and two overlapped rounds of 96 instead of one of 192 lost 5 %.)
   const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int widths[4] = {256, 192, 128, 64};
+  const int conc = gemm_sm_count() / 2;  // concurrently running CTA pairs
   int best = 0, best_tiles = 0;
   for (int i = 0; i < 4; ++i) {
     const int bn = widths[i];
     if (N % bn != 0) continue;
     const int tiles = m_pairs * (N / bn);
     if (best == 0) { best = bn; best_tiles = tiles; continue; }   // widest dividing width
-    if (best_tiles < 74 && tiles <= 74 && tiles > best_tiles) { best = bn; best_tiles = tiles; }
+    if (best_tiles < conc && tiles <= conc && tiles > best_tiles) { best = bn; best_tiles = tiles; }
   }
   return best;
 }
@@ -689,8 +741,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const bool pair = (forced_variant ? forced_variant : a.variant) != 1;
   int bn = a.block_n ? a.block_n
                      : (pair ? gemm_pick_pair_bn(a.M, a.N) : gemm_pick_block_n(a.M, a.N));
+  MSD_REQUIRE(pair || a.epilogue != EPI_GATED_GELU_SPLIT3,
+              "gemm: the split-precision gated epilogue exists in the CTA-pair kernel only");
   MSD_REQUIRE(bn == 64 || bn == 128 || bn == 256 || (pair && bn == 192) ||
-                  (pair && bn == 96 && a.epilogue != EPI_BF16 && a.epilogue != EPI_GATED_GELU),
+                  (pair && bn == 96 && !epi_is_bf16_out(a.epilogue)),
               "gemm: N=%d has no valid tile width (block_n %d)", a.N, bn);
   MSD_REQUIRE(a.N % bn == 0, "gemm: N=%d not a multiple of block_n=%d", a.N, bn);
   MSD_REQUIRE(a.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", a.ldo);
@@ -714,7 +768,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.pos_shift = a.pos_shift; d.dup_rows = a.dup_rows;
   if (pair) {
     CUtensorMap tout = ta, tres = ta;  // placeholders unless the epilogue is an fp32 one
-    if (a.epilogue != EPI_BF16 && a.epilogue != EPI_GATED_GELU) {
+    if (!epi_is_bf16_out(a.epilogue)) {
       const int rows = a.M + (a.epilogue == EPI_POS_F32 ? a.dup_rows : 0);
       if (int rc = make_tmap_f32_2d(&tout, a.out, rows, a.N, a.ldo, BLOCK_M)) return rc;
       if (a.epilogue == EPI_RESID_F32)

@@ -6,13 +6,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace msd {
 
 typedef __nv_bfloat16 bf16;
 
 // Global count of kernel launches issued through the launchers below (a graph
 // replay adds its node count).  Reported as bench.py's "gpu_launches".
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 // ---------------------------------------------------------------------------
 // Optional per-launch profiling (msd_profile_step): when a recorder is armed every launcher
@@ -40,7 +42,7 @@ struct ProfScope {
 // PDL is enabled (default; MSD_PDL=0 disables).  Works under stream capture (programmatic edges).
 // ---------------------------------------------------------------------------
 extern bool g_use_pdl;
-extern bool g_pdl_skip_next;  // next launch has a cross-stream dependency: plain launch
+extern thread_local bool g_pdl_skip_next;  // next launch (of this host thread) has a cross-stream dependency: plain launch
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                  cudaStream_t stream, Args&&... args) {
@@ -80,6 +82,9 @@ enum GemmEpilogue : int {
   EPI_GATED_GELU = 3,  // out bf16 [M, N/2]: per 64 acc columns, gelu(acc[0:32]) * acc[32:64]
   EPI_POS_F32 = 4,     // out f32 = acc + pos[(r % pos_rows - shift[r / pos_rows]) mod pos_rows]
                        //   optionally duplicated to out[r + dup_rows]
+  EPI_GATED_GELU_SPLIT3 = 5,  // fp32-accurate mode: g = gelu(acc[0:32]) * acc[32:64] with the exact
+                              //   tanh, written as bf16 [M, 3 * N/2] = [hi(g) | lo(g) | hi(g)]
+                              //   (the A operand of a 3 x bf16 split-precision GEMM); CTA-pair kernel
 };
 
 struct GemmArgs {
@@ -151,6 +156,15 @@ int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* ou
                    long long film_offset, int split3, cudaStream_t stream);
 
 constexpr int MSD_STEP_COLS = 16;  // floats per diffusion step in the sampler table
+// Per-call arguments of msd_sample that live in DEVICE memory, so that the captured step graph does
+// not depend on them (a new noise tensor / output buffer / seed does not force a re-capture).
+struct RunArgs {
+  const float* noise;        // [num_steps, B*N*n_dims] or nullptr -> generator(seed)
+  float* mel_out;            // written at step 0
+  unsigned long long seed;   // Philox stream (rng_kind 0)
+  int step;                  // current reverse-step index i (decremented by the sampler kernel)
+  unsigned int done;         // sampler blocks that have finished reading `step` (kept at 0)
+};
 struct SamplerArgs {
   const float* eps;       // [(passes*B)*N, n_dims] rows: cond block then uncond block
   float* z;               // [B*N*n_dims] state, updated in place
@@ -171,9 +185,11 @@ struct SamplerArgs {
   // i + 1 fold_in(key, i)), device memory
   int rng_kind;
   const uint32_t* rng_keys;
+  // when non-null: noise / mel_out / seed / step are read from here (device memory) instead of the
+  // fields above, and the last block to finish decrements run->step (the step advance)
+  RunArgs* run;
 };
 int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream);
-int launch_step_advance(int* step, cudaStream_t stream);
 
 // z0 = init (copy or philox normal), plus its [hi | lo | hi] split.
 // rng_kind / rng_keys as in SamplerArgs (keys row 0 is used)
@@ -187,13 +203,34 @@ int launch_embed_tokens(const int* tokens, const float* emb, const float* pos, f
 // ctx features -> clip, scale to [-1,1], [hi | lo | hi] split for the input projection
 int launch_scale_split(const float* feat, bf16* out_split, long long rows, int n_dims, float fmin,
                        float fmax, cudaStream_t stream);
+// fp32 rows [rows, cols] -> bf16 [rows, 3 * cols] = [hi | lo | hi]
+int launch_split3_rows(const float* src, bf16* out_split, long long rows, int cols,
+                       cudaStream_t stream);
 // key-mask bit words + terminal-relative roll amounts
 int launch_build_masks(const int* tokens, const int* ctx_mask, int B, int T, int C,
                        uint32_t* bits /*[B,(T+C)/32]*/, int* ctx_seq_len /*[B]*/,
                        int terminal_relative, cudaStream_t stream);
 // fp32 rows -> bf16 rows (encodings), with row remap b*src_len+t -> b*dst_len+dst_off+t
 int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src_len, int d,
-                              bf16* out, int dst_len, int dst_off, cudaStream_t stream);
+                              bf16* out, int dst_len, int dst_off, cudaStream_t stream,
+                              int split3 = 0);
+
+// ---------------------------------------------------------------------------
+// fp32 attention (the fp32-accurate mode of BASELINE config 2): same contract as AttnArgs'
+// kernel, but Q / K / V are fp32, every product and the softmax are fp32 (exact expf), and the
+// output is written as bf16 [rows, 3 * ldo_third] = [hi | lo | hi] of the fp32 result, i.e. the A
+// operand of the split-precision output projection.  SIMT (CUDA-core) kernel: accuracy mode.
+// ---------------------------------------------------------------------------
+struct AttnF32Args {
+  const float* Q; int ldq;
+  const float* K; int ldk;
+  const float* V; int ldv;
+  bf16* O; int o_third;      // O row stride = 3 * o_third; head h -> columns h*64 of each third
+  int nbatch, heads, Lq, Lk;
+  const uint32_t* mask_bits; int mask_stride_words;
+  int kv_batch_rows, kv_row0;  // as in AttnArgs
+};
+int launch_attention_f32(const AttnF32Args& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // Load-time kernels
@@ -202,9 +239,10 @@ int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src
 // part: 0 = bf16(w), 1 = bf16(w - bf16(w)) (low half of the split).
 int launch_pack_weight(const float* W, int K, int N, bf16* dst, int ldd, int n_off, int k_off,
                        int part, cudaStream_t stream);
-// Gated-MLP pack: dst rows interleave 32 columns of W0 then 32 of W1.
+// Gated-MLP pack: dst rows interleave 32 columns of W0 then 32 of W1; columns [k_off, k_off + K)
+// receive part 0 (bf16(w)) or part 1 (bf16(w - bf16(w))).
 int launch_pack_gated(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int k_off = 0, int part = 0);
 // C[M,N] = act(A[M,K] * B[K,N]) fp32 SIMT (act: 0 none, 1 swish)
 int launch_sgemm_f32(const float* A, const float* B, float* C, int ldc, int M, int N, int K,
                      int act, cudaStream_t stream);
@@ -212,7 +250,12 @@ int launch_sgemm_f32(const float* A, const float* B, float* C, int ldc, int M, i
 int launch_f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t stream);
 int launch_bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t stream);
 int launch_mask_bits(const int* mask, int nb, int L, uint32_t* bits, cudaStream_t stream);
+// dst [rows, cols] f32 = src[r * ld + c] (+ src[r * ld + lo_off + c] when lo_off > 0)
+int launch_bf16_rows_to_f32(const bf16* src, int ld, int lo_off, float* dst, long long rows, int cols,
+                            cudaStream_t stream);
 // out[0..n) = jax.random.normal(key, [n]) for key = (k0, k1); n a multiple of 8 (test hook)
 int launch_jax_normal(uint32_t k0, uint32_t k1, long long n, float* out, cudaStream_t stream);
+// the raw uint32 words the normals above are made from (same in-kernel code path)
+int launch_jax_bits(uint32_t k0, uint32_t k1, long long n, uint32_t* out, cudaStream_t stream);
 
 }  // namespace msd

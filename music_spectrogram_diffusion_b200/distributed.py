@@ -41,7 +41,10 @@ def predict_sharded(predict_fn: PredictFn, tokens: torch.Tensor, ctx: torch.Tens
   n = tokens.shape[0]
   lo, hi = shard_range(n, world, rank)
   if hi > lo:
-    mine = predict_fn(tokens[lo:hi], ctx[lo:hi], ctx_mask[lo:hi], seed + lo)
+    # NOTE: the noise of a batch is one jax.random draw over the whole [b, frames, dims] block
+    # (diffusion_utils.py:462), so the result depends on how segments are grouped into calls; the
+    # same seed is used for every block, like a reference run at that per-host batch size.
+    mine = predict_fn(tokens[lo:hi], ctx[lo:hi], ctx_mask[lo:hi], seed)
   else:
     mine = None
   if world == 1:
@@ -86,7 +89,9 @@ def synthesize_song(predict_fn: PredictFn, token_segments: Sequence[torch.Tensor
       mask = torch.zeros(1, context_frames, dtype=torch.int32, device=device) if first else \
           torch.ones(1, context_frames, dtype=torch.int32, device=device)
       toks = token_segments[k].to(device).reshape(1, -1)
-      pred = predict_fn(toks, prev, mask, seed + k)
+      # one constant seed for every segment, as beam/evaluation.py:209 (`predict(batch)`, i.e.
+      # seed 0 each time) and song.synthesize_song do: the relay is the same song on any world size
+      pred = predict_fn(toks, prev, mask, seed)
       mine.append((k, pred))
       prev = pred[:1].clone()  # own buffer: later recv()s must not overwrite a stored result
       if k + 1 < n_seg and world > 1:

@@ -20,14 +20,22 @@ from music_spectrogram_diffusion_b200 import _native
 from music_spectrogram_diffusion_b200.config import DiffusionConfig, T5Config
 
 
+PRECISIONS = {'bf16': 0, 'fp32_accurate': 1}
+
+
 def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int,
                     targets_length: int, context_length: int, max_batch: int,
                     n_dims: int = 128, feature_min: float = math.log(1e-5),
-                    feature_max: float = 4.0, rng: str = 'jax') -> _native.MsdConfig:
+                    feature_max: float = 4.0, rng: str = 'jax',
+                    precision: str = 'bf16') -> _native.MsdConfig:
   """Translate the reference's config objects into `struct msd_config`.  rng: 'jax' (the
-  threefry stream of jax.random.PRNGKey(seed), as the reference draws its noise) or 'philox'."""
+  threefry stream of jax.random.PRNGKey(seed), as the reference draws its noise) or 'philox'.
+  precision: 'bf16' (tensor-core operands in bf16, the fast path) or 'fp32_accurate' (3 x bf16
+  split-precision dense layers + fp32 attention: what T5Config.dtype = float32 asks for)."""
   if rng not in ('jax', 'philox'):
     raise ValueError(f'unknown rng {rng!r}')
+  if precision not in PRECISIONS:
+    raise ValueError(f'unknown precision {precision!r} (expected one of {sorted(PRECISIONS)})')
   if tuple(t5.mlp_activations) != ('gelu', 'linear'):
     raise NotImplementedError(
         f'mlp_activations={t5.mlp_activations}: only the gated-GELU MLP of the '
@@ -79,7 +87,7 @@ def make_msd_config(t5: T5Config, diffusion: DiffusionConfig, inputs_length: int
       sampler_beta_start=float(sched.start or 0.0), sampler_beta_stop=float(sched.stop or 0.0),
       train_beta_start=float(tsched.start or 0.0), train_beta_stop=float(tsched.stop or 0.0),
       cross_attend_style=styles[t5.decoder_cross_attend_style],
-      rng_kind={'philox': 0, 'jax': 1}[rng])
+      rng_kind={'philox': 0, 'jax': 1}[rng], precision=PRECISIONS[precision])
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
@@ -228,6 +236,47 @@ def op_rmsnorm_film(x: torch.Tensor, gamma: torch.Tensor,
   out = torch.empty_like(x)
   _native.check(lib.msd_op_rmsnorm_film(_ptr(x.contiguous()), _ptr(gamma), _ptr(film), rows, d,
                                         _ptr(out), _stream(x.device)), 'msd_op_rmsnorm_film')
+  return out
+
+
+EPILOGUES = {'bf16': 0, 'resid_f32': 2, 'gated_gelu': 3, 'pos_f32': 4, 'gated_gelu_split3': 5}
+
+
+def op_dense_epilogue(a: torch.Tensor, w: torch.Tensor, epilogue: str, block_n: int = 0,
+                      w1: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+                      pos: Optional[torch.Tensor] = None, pos_shift: Optional[torch.Tensor] = None,
+                      dup_rows: int = 0) -> torch.Tensor:
+  """The GEMM with one of its fused epilogues (kernels.h GemmEpilogue); see msd_op_dense_epilogue."""
+  lib = _native.load()
+  m, k = a.shape
+  n = w.shape[1]
+  out = torch.empty(m + dup_rows, n, dtype=torch.float32, device=a.device)
+  pos_rows = 0 if pos is None else pos.shape[0]
+  keep = [t.contiguous() if t is not None else None for t in (a, w, w1, resid, pos, pos_shift)]
+  _native.check(lib.msd_op_dense_epilogue(_ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), m, n, k,
+                                          EPILOGUES[epilogue], block_n, _ptr(keep[3]), _ptr(keep[4]),
+                                          pos_rows, _ptr(keep[5]), dup_rows, _ptr(out),
+                                          _stream(a.device)), 'msd_op_dense_epilogue')
+  return out
+
+
+def op_attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                     key_mask: Optional[torch.Tensor], heads: int) -> torch.Tensor:
+  lib = _native.load()
+  nb, lq, _ = q.shape
+  lk = k.shape[1]
+  out = torch.empty_like(q)
+  _native.check(lib.msd_op_attention_f32(_ptr(q.contiguous()), _ptr(k.contiguous()),
+                                         _ptr(v.contiguous()), _ptr(key_mask), nb, heads, lq, lk,
+                                         _ptr(out), _stream(q.device)), 'msd_op_attention_f32')
+  return out
+
+
+def op_jax_bits(seed: int, step: int, n: int, device: torch.device) -> torch.Tensor:
+  """Raw uint32 words of the device jax.random stream (as int32 storage; view as uint32)."""
+  out = torch.empty(n, dtype=torch.int32, device=device)
+  _native.check(_native.load().msd_op_jax_bits(seed, step, n, _ptr(out), _stream(device)),
+                'msd_op_jax_bits')
   return out
 
 

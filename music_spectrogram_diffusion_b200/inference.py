@@ -165,26 +165,30 @@ class InferenceModel:
   """Wrapper of the B200 engine with the reference's `InferenceModel` surface."""
 
   def __init__(self, checkpoint_path: str, gin_config: str, batch_size: int = 1,
-               device: int = 0, rng: str = 'jax'):
+               device: int = 0, rng: str = 'jax', precision: str = 'bf16'):
     t5, diff, lengths, codec = _build_from_gin(gin_config)
-    self._init_common(checkpoint_path, t5, diff, lengths, codec, batch_size, device, rng=rng)
+    self._init_common(checkpoint_path, t5, diff, lengths, codec, batch_size, device, rng=rng,
+                      precision=precision)
 
   @classmethod
   def from_config(cls, t5: config.T5Config, diffusion: config.DiffusionConfig,
                   sequence_length: Mapping[str, int], checkpoint_path: str = 'synthetic:0',
                   batch_size: int = 1, device: int = 0,
                   params: Optional[Dict[str, np.ndarray]] = None,
-                  rng: str = 'jax') -> 'InferenceModel':
+                  rng: str = 'jax', precision: str = 'bf16') -> 'InferenceModel':
     self = cls.__new__(cls)
     self._init_common(checkpoint_path, t5, diffusion, dict(sequence_length), EventCodecInfo(),
-                      batch_size, device, params, rng)
+                      batch_size, device, params, rng, precision)
     return self
 
   def _init_common(self, checkpoint_path, t5, diff, lengths, codec, batch_size, device,
-                   params=None, rng='jax'):
+                   params=None, rng='jax', precision='bf16'):
     if rng not in ('jax', 'philox'):
       raise ValueError(f'unknown rng {rng!r}')
+    if precision not in engine.PRECISIONS:
+      raise ValueError(f'unknown precision {precision!r}')
     self.rng = rng
+    self.precision = precision
     self.checkpoint_path = checkpoint_path
     self.batch_size = batch_size
     self.partitioner = _Partitioner()
@@ -257,7 +261,7 @@ class InferenceModel:
           self.model.module_config, self.model.diffusion_config, self.inputs_length,
           self.targets_length, self.targets_context_length, self.batch_size,
           self.audio_codec.n_dims, self.audio_codec.min_value, self.audio_codec.max_value,
-          rng=self.rng)
+          rng=self.rng, precision=self.precision)
       eng = engine.Engine(cfg, self._device_index)
       eng.load_weights(self._restore_from_checkpoint())
       self._params = None  # the engine holds the packed copy

@@ -84,7 +84,11 @@ def _unchunk(tree: Any) -> Any:
   """Reassemble flax's chunked arrays ({'__msgpack_chunked_array__': True, 'shape', 'chunks'})."""
   if isinstance(tree, dict):
     if tree.get(_CHUNK_MARK):
-      shape = tuple(tree['shape'])
+      sh = tree['shape']
+      # flax serialises the tuple as {'0': n, '1': m, ...} (serialization._tuple_to_dict); a
+      # plain list is accepted as well
+      shape = (tuple(int(sh[str(i)]) for i in range(len(sh))) if isinstance(sh, dict)
+               else tuple(int(v) for v in sh))
       chunks = tree['chunks']
       parts = [np.asarray(chunks[str(i)]).reshape(-1) for i in range(len(chunks))]
       return np.concatenate(parts).reshape(shape)
@@ -253,10 +257,16 @@ def _read_leaf(ckpt_dir: str, name: str, leaf: Any, dtype) -> np.ndarray:
   if _is_ts_spec(leaf):
     if leaf.get('driver') != 'zarr':
       raise CheckpointError(f'{name}: TensorStore driver {leaf.get("driver")!r} is not supported')
-    rel = leaf['kvstore']['path'] if isinstance(leaf['kvstore'], dict) else str(leaf['kvstore'])
-    # the spec may still carry the absolute path of the training job: fall back to its basename
-    cand = [os.path.join(ckpt_dir, rel), os.path.join(ckpt_dir, os.path.basename(rel.rstrip('/'))),
-            os.path.join(ckpt_dir, 'target.' + name.replace('/', '.'))]
+    # Local-file checkpoints keep the array directory in kvstore.path; checkpoints written to GCS
+    # (e.g. the published base_with_context/checkpoint_500000) carry kvstore = {'driver': 'gcs',
+    # 'bucket': ...} and a top-level 'path'.  Either may be absent or hold the training job's
+    # absolute path, so the basename and the conventional 'target.<name>' directory are tried too.
+    kv = leaf.get('kvstore')
+    rel = (kv.get('path') if isinstance(kv, dict) else (str(kv) if kv else None)) or leaf.get('path') or ''
+    rel = str(rel)
+    cand = [os.path.join(ckpt_dir, 'target.' + name.replace('/', '.'))]
+    if rel:
+      cand = [os.path.join(ckpt_dir, rel), os.path.join(ckpt_dir, os.path.basename(rel.rstrip('/')))] + cand
     apath = next((c for c in cand if os.path.isdir(c)), None)
     if apath is None:
       raise CheckpointError(f'{name}: array directory {rel!r} not found under {ckpt_dir}')

@@ -77,7 +77,7 @@ def test_two_ranks_match_single_process():
   tokens = torch.randint(1, 100, (n, TOK), generator=g)
   ctx_t = torch.randn(n, FRAMES, DIMS, generator=g)
   mask = torch.ones(n, FRAMES, dtype=torch.int32)
-  want_full = torch.cat([fake_predict(tokens[a:b], ctx_t[a:b], mask[a:b], 3 + a)
+  want_full = torch.cat([fake_predict(tokens[a:b], ctx_t[a:b], mask[a:b], 3)
                          for a, b in (D.shard_range(n, world, r) for r in range(world))])
   segs = [torch.randint(1, 100, (TOK,), generator=g) for _ in range(5)]
   want_song = D.synthesize_song(fake_predict, segs, FRAMES, DIMS, torch.device('cpu'), seed=1)
@@ -85,5 +85,11 @@ def test_two_ranks_match_single_process():
     np.testing.assert_allclose(results[r][0], want_full.numpy(), rtol=0, atol=0)
   np.testing.assert_allclose(results[0][1], want_song.numpy(), rtol=0, atol=0)
   assert results[1][1] is None
+  # the relay is the single-process chain with ONE seed for every segment (beam/evaluation.py:209)
+  prev = torch.zeros(1, FRAMES, DIMS)
+  for k, seg in enumerate(segs):
+    m = torch.zeros(1, FRAMES, dtype=torch.int32) if k == 0 else torch.ones(1, FRAMES, dtype=torch.int32)
+    prev = fake_predict(seg.reshape(1, -1), prev, m, 1)
+    np.testing.assert_array_equal(want_song[0, k * FRAMES:(k + 1) * FRAMES].numpy(), prev[0].numpy())
   # the chain really chains: segment 1 depends on segment 0's output
   assert not np.allclose(want_song[0, :FRAMES].numpy(), want_song[0, FRAMES:2 * FRAMES].numpy())

@@ -106,8 +106,9 @@ def test_sample_matches_oracle(cuda_device, tiny, sampler, weight):
   span = oc.max_value - oc.min_value
   err = (mel - ref).abs() / span * 2.0     # normalised [-1, 1] units
   assert torch.isfinite(mel).all()
-  # tolerance (bf16 operand path): mean |d| <= 3e-2 in normalised units
-  assert err.mean().item() < 3e-2, f'mean {err.mean().item()} max {err.max().item()}'
+  # tolerance (bf16 operand path): mean |d| <= 3e-2 in normalised units, plus p99 and
+  # the share of elements off by more than 0.1
+  H.assert_trajectory_close(err, f'tiny {sampler} w={weight}')
   eng.close()
 
 
@@ -163,7 +164,7 @@ def test_sampler_variants_match_oracle(cuda_device, tiny, name):
   span = oc.max_value - oc.min_value
   err = (mel - ref).abs() / span * 2.0
   assert torch.isfinite(mel).all()
-  assert err.mean().item() < 3e-2, f'{name}: mean {err.mean().item()} max {err.max().item()}'
+  H.assert_trajectory_close(err, f'variant {name}')
   eng.close()
 
 
@@ -197,7 +198,8 @@ def test_sum_cross_attends_matches_oracle(cuda_device):
   mel = eng.sample(z, noise.to(cuda_device)).cpu()
   ref, _ = O.predict_batch_with_aux(p, oc, cb, init_z, noise)
   err = (mel - ref).abs() / (oc.max_value - oc.min_value) * 2.0
-  assert torch.isfinite(mel).all() and err.mean().item() < 3e-2, (err.mean().item(), err.max().item())
+  assert torch.isfinite(mel).all()
+  H.assert_trajectory_close(err, 'sum_cross_attends')
   eng.close()
 
 
@@ -290,7 +292,7 @@ def test_small_model_one_segment_ten_steps(cuda_device):
                                     init_z, noise)
   err = (mel - ref).abs() / (oc.max_value - oc.min_value) * 2.0
   assert mel.shape == (1, 256, 128) and torch.isfinite(mel).all()
-  assert err.mean().item() < 3e-2, (err.mean().item(), err.max().item())
+  H.assert_trajectory_close(err, 'small, 1 segment, 10 steps')
   eng.close()
 
 
@@ -334,7 +336,7 @@ def test_inference_model_predict_matches_golden_fixture(cuda_device):
   assert scores.shape == (g['tokens'].shape[0],) and not scores.any()
   span = 4.0 - np.log(1e-5)
   err = np.abs(mel - g['mel']) / span * 2.0
-  assert err.mean() < 3e-2, (err.mean(), err.max())
+  H.assert_trajectory_close(err, 'tiny golden fixture through InferenceModel.predict')
   with pytest.raises(ValueError):
     model.predict(dict(batch, encoder_input_tokens=g['tokens'][:, :64]))
 
@@ -410,9 +412,9 @@ def test_chained_song_single_gpu(cuda_device, tiny):
   for k, s in enumerate(segs):
     b = dict(encoder_input_tokens=s.numpy()[None], encoder_continuous_inputs=prev,
              encoder_continuous_mask=np.full((1, C), 0 if k == 0 else 1, np.int32))
-    prev, _ = model.predict(b, seed=5 + k)
+    prev, _ = model.predict(b, seed=5)
     outs.append(prev)
-  np.testing.assert_allclose(song.cpu().numpy(), np.concatenate(outs, axis=1), atol=1e-5)
+  np.testing.assert_array_equal(song.cpu().numpy(), np.concatenate(outs, axis=1))
 
 
 @pytest.mark.parametrize('steps', [20, 1000])
@@ -440,7 +442,125 @@ def test_base_with_context_matches_oracle_fixture(cuda_device, steps):
   mel, _ = model.predict(batch, seed=int(g['seed']))
   span = 4.0 - np.log(1e-5)
   err = np.abs(mel - g['mel']) / span * 2.0
-  print(f'base {steps} steps: mean|d|={err.mean():.3e} p99={np.quantile(err, 0.99):.3e} '
-        f'max={err.max():.3e}')
   assert np.isfinite(mel).all()
-  assert err.mean() < 3e-2, (err.mean(), err.max())
+  H.assert_trajectory_close(err, f'base_with_context, 1 segment, {steps} steps')
+
+
+def test_base_with_context_batch8_matches_oracle_fixture(cuda_device):
+  """BASELINE config 3 -- the configuration bench.py measures: base_with_context, batch of 8
+  segments through InferenceModel.predict(batch_size=8) (256-wide CTA-pair GEMM tiles at M = 4096,
+  the long/short cross-attention split inside the captured step graph), mixed token padding, one
+  fully masked and one partially filled context, against the fp32 oracle (graph as written).
+  Fixture: tests/golden/base_b8_predict_20.npz (tests/golden/make_base_b8_golden.py)."""
+  import os
+  from music_spectrogram_diffusion_b200 import inference
+  path = os.path.join(os.path.dirname(__file__), 'golden', 'base_b8_predict_20.npz')
+  g = np.load(path)
+  t5 = config.t5_base()
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = int(g['steps'])
+  diff.classifier_free_guidance.eval_condition_weight = float(g['cond_weight'])
+  lengths = dict(config.TASK_FEATURE_LENGTHS_CONTEXT)
+  model = inference.InferenceModel.from_config(t5, diff, lengths,
+                                               f'synthetic:{int(g["weight_seed"])}', batch_size=8,
+                                               rng='philox')
+  batch = H.base_b8_batch(lengths, int(g['batch_seed']))
+  mel, _ = model.predict(batch, seed=int(g['seed']))
+  assert mel.shape == (8, 256, 128) and np.isfinite(mel).all()
+  span = 4.0 - np.log(1e-5)
+  err = np.abs(mel - g['mel']) / span * 2.0
+  H.assert_trajectory_close(err, 'base_with_context, 8 segments, 20 steps')
+  for seg in range(8):   # no segment hides behind the batch average
+    H.assert_trajectory_close(err[seg], f'  segment {seg}')
+
+
+# ---- fp32-accurate mode (BASELINE config 2) ------------------------------------------------------
+def test_fp32_accurate_decoder_forward(cuda_device, tiny):
+  """precision='fp32_accurate': one decoder forward (network.py:360-457) to ~1e-4 of the fp32
+  oracle (max|d eps| <= 1e-4 rms for the fp32-accurate path; the 3 x bf16 split keeps
+  ~16 mantissa bits per operand), conditioned and unconditioned, plus the encoders."""
+  t5, params = tiny
+  B, steps = 3, 16
+  toks, ctx, cmask = H.make_batch(B, T, C, ctx_masks=[1, 0, 1])
+  cmask[2, 40:] = 0
+  eng = H.build_engine(t5, T, N, C, B, steps, 2.0, params, precision='fp32_accurate')
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'], b['encoder_continuous_mask'])
+  oc = H.oracle_config(t5, steps, 2.0)
+  P = O.params_to(params)
+  cb = H.torch_batch(toks, ctx, cmask)
+  encs = O.encode(P, oc, cb['encoder_input_tokens'],
+                  O.scale_features(cb['encoder_continuous_inputs'], oc, clip=True),
+                  cb['encoder_continuous_mask'])
+  want = torch.cat([encs[0][0], encs[1][0]], dim=1)
+  valid = torch.cat([encs[0][1], encs[1][1]], dim=1) > 0
+  err = ((eng.encodings().cpu() - want).abs() * valid.unsqueeze(-1)).max().item()
+  assert err < 2e-3, f'encodings: {err}'          # stored as hi + lo: 16 mantissa bits of O(10) values
+  z = torch.randn(B, N, 128, generator=torch.Generator().manual_seed(3))
+  for conditioned in (True, False):
+    flag = 1.0 if conditioned else 0.0
+    for step_i in (steps - 1, 5, 0):
+      got = eng.decode_eps(z.to(cuda_device), step_i, conditioned).cpu()
+      t = np.float32(step_i + 1.0) / np.float32(steps)
+      ref = O.decode(P, oc, [(e * flag, m * flag) for e, m in encs], z, torch.full((B,), float(t)))
+      rel = ((got - ref).abs().max() / ref.pow(2).mean().sqrt()).item()
+      assert rel < 2e-3, f'cond={conditioned} step {step_i}: {rel}'
+  eng.close()
+
+
+@pytest.mark.parametrize('sampler,weight,style', [('ddpm', 2.0, 'concat_encodings'),
+                                                   ('ddim', 2.0, 'concat_encodings'),
+                                                   ('ddpm', 1.0, 'concat_encodings'),
+                                                   ('ddpm', 2.0, 'sum_cross_attends')])
+def test_fp32_accurate_sample_matches_oracle(cuda_device, sampler, weight, style):
+  """Full trajectories in the fp32-accurate mode: mean |d| <= 1e-3 normalised (SURVEY 8d's fp32
+  tolerance), an order of magnitude inside the bf16 path's 3e-2."""
+  t5 = config.t5_tiny()
+  t5.decoder_cross_attend_style = style
+  params = weights.synthetic_params(t5, T, N, C, seed=0 if style == 'concat_encodings' else 5)
+  B, steps = 2, 12
+  toks, ctx, cmask = H.make_batch(B, T, C)
+  init_z, noise = H.make_noise(steps, B, N)
+  eng = H.build_engine(t5, T, N, C, B, steps, weight, params, sampler=sampler,
+                       precision='fp32_accurate')
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'], b['encoder_continuous_mask'])
+  mel = eng.sample(init_z.to(cuda_device), noise.to(cuda_device)).cpu()
+  oc = H.oracle_config(t5, steps, weight, sampler=sampler)
+  ref, _ = O.predict_batch_with_aux(O.params_to(params), oc, H.torch_batch(toks, ctx, cmask),
+                                    init_z, noise)
+  err = (mel - ref).abs() / (oc.max_value - oc.min_value) * 2.0
+  H.assert_trajectory_close(err, f'fp32-accurate tiny {sampler} w={weight} {style}',
+                            mean=1e-3, p99=1e-2, share_01=2e-3)
+  eng.close()
+
+
+@pytest.mark.parametrize('steps', [20, 1000])
+def test_fp32_accurate_base_with_context_matches_oracle_fixture(cuda_device, steps):
+  """BASELINE config 2 as written: base_with_context, 1 segment, fp32 vs the reference tolerance
+  (mean |d| <= 1e-3 normalised over the full trajectory)."""
+  import os
+  import bench
+  from music_spectrogram_diffusion_b200 import inference
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', f'base_predict_{steps}.npz'))
+  t5 = config.t5_base()
+  diff = config.DiffusionConfig()
+  diff.sampler.schedule.num_steps = int(g['steps'])
+  diff.classifier_free_guidance.eval_condition_weight = float(g['cond_weight'])
+  lengths = dict(config.TASK_FEATURE_LENGTHS_CONTEXT)
+  model = inference.InferenceModel.from_config(
+      t5, diff, lengths, f'synthetic:{int(g["weight_seed"])}', batch_size=1, rng='philox',
+      precision='fp32_accurate')
+  batch = bench.synthetic_batch(1, lengths, seed=int(g['batch_seed']))
+  # the very draws the fixture was made with (oracle/philox.py, numpy), injected: the device
+  # generator agrees with numpy only to an ulp or two (sincospif vs float64 cos), which this
+  # tolerance would see
+  from oracle import philox
+  shape, seed = (1, 256, 128), int(g['seed'])
+  init_z = philox.init_z(seed, shape)
+  noise = np.stack([philox.step_noise(seed, i, shape) for i in range(steps)])
+  mel, _ = model.predict(batch, seed=seed, init_z=init_z, noise=noise)
+  err = np.abs(mel - g['mel']) / (4.0 - np.log(1e-5)) * 2.0
+  assert np.isfinite(mel).all()
+  H.assert_trajectory_close(err, f'fp32-accurate base_with_context, 1 segment, {steps} steps',
+                            mean=1e-3, p99=1e-2, share_01=2e-3)

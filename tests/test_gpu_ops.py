@@ -119,3 +119,152 @@ def test_layer_norm_film(cuda_device, rows, d, film):
   err = (got - want).abs().max().item()
   assert err < 4e-2, f'max err {err}'   # bf16 output rounding of O(4) values
   assert (got - bf16_round(want)).abs().max().item() < 2e-2
+
+
+# ---- fused GEMM epilogues (kernels.h GemmEpilogue), each at the decoder's B = 8 height ----------
+def _dense_inputs(M, N, K, seed):
+  g = torch.Generator().manual_seed(seed)
+  a = bf16_round(torch.randn(M, K, generator=g))
+  w = bf16_round(torch.randn(K, N, generator=g) / np.sqrt(K))
+  return g, a, w
+
+
+@pytest.mark.parametrize('block_n', [0, 64, 128, 192, 256])
+@pytest.mark.parametrize('M,N,K', [(4096, 2304, 768), (512, 768, 768), (4096, 768, 2048)])
+def test_epilogue_bf16(cuda_device, M, N, K, block_n):
+  """EPI_BF16 (q/k/v projections, layers.py:262-264): bf16(a w) against the fp64 product."""
+  from music_spectrogram_diffusion_b200 import engine
+  if block_n and N % block_n:
+    pytest.skip('tile width does not divide N')
+  _, a, w = _dense_inputs(M, N, K, M + N + K + 1)
+  got = engine.op_dense_epilogue(a.to(cuda_device), w.to(cuda_device), 'bf16', block_n).cpu()
+  want = O.dense_general(a.double(), w.double()).float()
+  assert torch.equal(got, bf16_round(got))                       # really a bf16 result
+  # one bf16 rounding of an O(1) value + fp32 accumulation error
+  assert (got - want).abs().max().item() < 2.0 ** -8 * max(1.0, want.abs().max().item()) + 2e-4 * np.sqrt(K)
+
+
+@pytest.mark.parametrize('block_n', [0, 64, 96, 128, 192, 256])
+@pytest.mark.parametrize('M,N,K', [(4096, 768, 768), (512, 768, 2048), (4096, 768, 2048)])
+def test_epilogue_residual_f32(cuda_device, M, N, K, block_n):
+  """EPI_RESID_F32 (x + out-projection / wo, network.py:186-193, 252-256), TMA-loaded residual
+  chunks and TMA stores; in place like the engine uses it."""
+  from music_spectrogram_diffusion_b200 import engine
+  if block_n and N % block_n:
+    pytest.skip('tile width does not divide N')
+  g, a, w = _dense_inputs(M, N, K, M + N + K + 2)
+  resid = torch.randn(M, N, generator=g) * 3
+  got = engine.op_dense_epilogue(a.to(cuda_device), w.to(cuda_device), 'resid_f32', block_n,
+                                 resid=resid.to(cuda_device)).cpu()
+  want = (O.dense_general(a.double(), w.double()) + resid.double()).float()
+  assert (got - want).abs().max().item() < 2e-4 * np.sqrt(K)
+
+
+@pytest.mark.parametrize('block_n', [0, 64, 128, 256])
+@pytest.mark.parametrize('dup', [False, True])
+@pytest.mark.parametrize('shifted', [False, True])
+def test_epilogue_position_f32(cuda_device, block_n, dup, shifted):
+  """EPI_POS_F32: input projection + position table rows (network.py:327-334 terminal-relative
+  roll, 420-427), optionally duplicated into the unconditional rows (dup_rows)."""
+  from music_spectrogram_diffusion_b200 import engine
+  nseq, L, N, K = 8, 256, 768, 384
+  M = nseq * L
+  g, a, w = _dense_inputs(M, N, K, 4242 + block_n)
+  pos = torch.randn(L, N, generator=g)
+  shift = torch.tensor([0, 40, 255, 1, 128, 0, 77, 200], dtype=torch.int32) if shifted else None
+  got = engine.op_dense_epilogue(a.to(cuda_device), w.to(cuda_device), 'pos_f32', block_n,
+                                 pos=pos.to(cuda_device),
+                                 pos_shift=None if shift is None else shift.to(cuda_device),
+                                 dup_rows=M if dup else 0).cpu()
+  y = O.dense_general(a.double(), w.double()).view(nseq, L, N)
+  for s_ in range(nseq):
+    sh = int(shift[s_]) if shifted else 0
+    # row r of sequence s gets pos[(r - shift) mod L] == roll(arange(L), shift)[r]
+    y[s_] += pos.double()[torch.roll(torch.arange(L), sh, 0)]
+  want = y.view(M, N).float()
+  assert got.shape[0] == (2 * M if dup else M)
+  assert (got[:M] - want).abs().max().item() < 2e-4 * np.sqrt(K)
+  if dup:
+    assert torch.equal(got[M:], got[:M])
+
+
+@pytest.mark.parametrize('block_n', [0, 64, 128, 256])
+@pytest.mark.parametrize('M,F,K', [(4096, 2048, 768), (512, 1024, 512)])
+def test_epilogue_gated_gelu(cuda_device, M, F, K, block_n):
+  """EPI_GATED_GELU: gelu_tanh(x wi_0) * (x wi_1) (layers.py:483-509) with the wi_0 / wi_1 rows
+  interleaved in 32-column groups and tanh.approx in the epilogue; the tanh.approx error
+  (abs ~5e-4 on tanh) is bounded here in isolation."""
+  from music_spectrogram_diffusion_b200 import engine
+  if block_n and (2 * F) % block_n:
+    pytest.skip('tile width does not divide 2F')
+  g, a, w0 = _dense_inputs(M, F, K, M + F + K + 3)
+  w1 = bf16_round(torch.randn(K, F, generator=g) / np.sqrt(K))
+  a = a * 2.0   # pre-activations with a few sigma of range (|u| up to ~8)
+  got = engine.op_dense_epilogue(a.to(cuda_device), w0.to(cuda_device), 'gated_gelu', block_n,
+                                 w1=w1.to(cuda_device)).cpu()
+  h0, h1 = O.dense_general(a.double(), w0.double()), O.dense_general(a.double(), w1.double())
+  want = (O.gelu_tanh(h0) * h1).float()
+  err = (got - want).abs()
+  tol = 2.0 ** -8 * want.abs() + 1.5e-3 * h1.abs().float() + 1e-3   # bf16 rounding + tanh.approx * |gate|
+  assert (err <= tol).all(), (err - tol).max().item()
+  assert err.mean().item() < 4e-3
+
+
+@pytest.mark.parametrize('M,F,K', [(512, 2048, 768), (256, 256, 128)])
+def test_epilogue_gated_gelu_split_precision(cuda_device, M, F, K):
+  """EPI_GATED_GELU_SPLIT3 (fp32-accurate mode): unrounded fp32 operands through the 3 x bf16
+  split GEMM, exact tanh, [hi | lo | hi] output: ~2^-16 relative."""
+  from music_spectrogram_diffusion_b200 import engine
+  g = torch.Generator().manual_seed(M + F + K)
+  a = torch.randn(M, K, generator=g) * 2.0
+  w0 = torch.randn(K, F, generator=g) / np.sqrt(K)
+  w1 = torch.randn(K, F, generator=g) / np.sqrt(K)
+  got = engine.op_dense_epilogue(a.to(cuda_device), w0.to(cuda_device), 'gated_gelu_split3', 0,
+                                 w1=w1.to(cuda_device)).cpu()
+  want = (O.gelu_tanh(O.dense_general(a.double(), w0.double())) *
+          O.dense_general(a.double(), w1.double())).float()
+  err = (got - want).abs().max().item()
+  assert err < 3e-4 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
+    (1, 1, 128, 128, False), (2, 3, 256, 384, True), (1, 2, 256, 2304, True),
+    (3, 2, 128, 256, True), (2, 12, 256, 256, False)])
+def test_dot_product_attention_fp32(cuda_device, nb, heads, Lq, Lk, masked):
+  """The fp32 attention of the fp32-accurate mode against the oracle on UNROUNDED fp32 inputs,
+  large logits included (no 1/sqrt(d) scaling in this model)."""
+  from music_spectrogram_diffusion_b200 import engine
+  g = torch.Generator().manual_seed(nb * 31 + Lk)
+  w = heads * 64
+  q = torch.randn(nb, Lq, w, generator=g) * 0.7
+  k = torch.randn(nb, Lk, w, generator=g) * 0.7
+  v = torch.randn(nb, Lk, w, generator=g)
+  mask = bias = m4 = None
+  if masked:
+    mask = (torch.rand(nb, Lk, generator=g) > 0.3).to(torch.int32)
+    mask[0, Lk // 2:] = 0
+    if nb > 2:
+      mask[2, :] = 0
+    m4 = O.make_attention_mask(torch.ones(nb, Lq), mask.float())
+    bias = torch.where(m4 > 0, torch.zeros_like(m4), torch.full_like(m4, -1e10))
+  want = O.dot_product_attention(q.double().view(nb, Lq, heads, 64), k.double().view(nb, Lk, heads, 64),
+                                 v.double().view(nb, Lk, heads, 64),
+                                 None if bias is None else bias.double()).reshape(nb, Lq, w).float()
+  if masked:
+    want = O.zero_activations_if_masked(want, m4)
+  got = engine.op_attention_f32(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device),
+                                None if mask is None else mask.to(cuda_device), heads).cpu()
+  err = (got - want).abs().max().item()
+  assert torch.isfinite(got).all() and err < 1e-4, err
+
+
+def test_device_threefry_bits_are_exact(cuda_device):
+  """Integer work is bit-exact: the uint32 words of the device jax.random stream (before the
+  float transform) == jax_rng.random_bits for PRNGKey(seed) and for fold_in(key, i)."""
+  from music_spectrogram_diffusion_b200 import engine, jax_rng as J
+  for seed, step, n in ((0, -1, 4096), (7, 0, 65536), (123456789, 999, 2 * 256 * 128),
+                        ((5 << 32) | 77, 3, 8), (31337, 500, 8 * 256 * 128)):
+    key = J.prng_key(seed) if step < 0 else J.fold_in(J.prng_key(seed), step)
+    want = J.random_bits(key, n)
+    got = engine.op_jax_bits(seed, step, n, cuda_device).cpu().numpy().view(np.uint32)
+    np.testing.assert_array_equal(got, want)

@@ -137,15 +137,16 @@ def test_c_abi_exports_every_declared_symbol(native_lib):
   assert declared == bound, (declared ^ bound)
   for name in declared:
     assert hasattr(native_lib, name), name
-  assert native_lib.msd_abi_version() == 2
+  assert native_lib.msd_abi_version() == _native.ABI_VERSION == 3
   assert isinstance(native_lib.msd_last_error(), bytes)
 
 
 def test_struct_layout_matches_header():
-  """msd_config (ABI 2): 17 int32, 4 float, 4 int32, 5 float, 2 int32, no padding; msd_tensor:
+  """msd_config (ABI 3): 17 int32, 4 float, 4 int32, 5 float, 3 int32, no padding; msd_tensor:
   ptr, ptr, int32, int64[4]."""
-  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4 + 4 * 4 + 5 * 4 + 4 + 4
+  assert ctypes.sizeof(_native.MsdConfig) == 17 * 4 + 4 * 4 + 4 * 4 + 5 * 4 + 4 + 4 + 4
   assert _native.MsdConfig.rng_kind.offset == 124
+  assert _native.MsdConfig.precision.offset == 128
   assert _native.MsdConfig.cross_attend_style.offset == 120
   assert _native.MsdConfig.max_decoder_noise_time.offset == 68
   assert _native.MsdConfig.model_output.offset == 84
@@ -236,11 +237,29 @@ def test_header_is_plain_c(tmp_path):
   src = tmp_path / 'layout.c'
   src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "msd_b200.h"\n'
                  'int main(void) { printf("%zu %zu %zu %zu %d\\n", sizeof(msd_config), '
-                 'offsetof(msd_config, rng_kind), sizeof(msd_tensor), offsetof(msd_tensor, shape), '
+                 'offsetof(msd_config, precision), sizeof(msd_tensor), offsetof(msd_tensor, shape), '
                  'MSD_B200_ABI_VERSION); return 0; }\n')
   exe = tmp_path / 'layout'
   subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
                  check=True)
   out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
-  assert [int(x) for x in out] == [ctypes.sizeof(_native.MsdConfig), _native.MsdConfig.rng_kind.offset,
-                                   ctypes.sizeof(_native.MsdTensor), _native.MsdTensor.shape.offset, 2]
+  assert [int(x) for x in out] == [ctypes.sizeof(_native.MsdConfig), _native.MsdConfig.precision.offset,
+                                   ctypes.sizeof(_native.MsdTensor), _native.MsdTensor.shape.offset,
+                                   _native.ABI_VERSION]
+
+
+def test_stale_library_is_refused(monkeypatch, native_lib):
+  """load() checks msd_abi_version() against the binding (a stale .so from an older header must not
+  be driven through mismatched struct layouts)."""
+  monkeypatch.setattr(_native, '_lib', None)
+  monkeypatch.setattr(_native, 'ABI_VERSION', _native.ABI_VERSION + 1)
+  with pytest.raises(_native.MsdError, match='stale'):
+    _native.load()
+
+
+def test_precision_names():
+  t5, d = config.t5_base(), config.DiffusionConfig()
+  assert engine.make_msd_config(t5, d, 2048, 256, 256, 1).precision == 0
+  assert engine.make_msd_config(t5, d, 2048, 256, 256, 1, precision='fp32_accurate').precision == 1
+  with pytest.raises(ValueError, match='unknown precision'):
+    engine.make_msd_config(t5, d, 2048, 256, 256, 1, precision='fp16')

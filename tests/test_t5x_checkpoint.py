@@ -119,3 +119,43 @@ def test_missing_array_and_shape_mismatch_are_loud(tmp_path):
     weights.check_params(bad, t5, 128, 128, 128, 128)
   with pytest.raises(tc.CheckpointError):
     tc.load_t5x_checkpoint(str(tmp_path / 'nope'))
+
+
+def test_gcs_style_spec_and_dict_shaped_chunks(tmp_path):
+  """Checkpoints written to GCS (the published ones) carry kvstore = {'driver': 'gcs', 'bucket':
+  ...} plus a top-level 'path' instead of kvstore.path; flax writes a chunked array's shape as
+  {'0': n, '1': m}.  Both forms restore; a spec without any usable path falls back to the
+  conventional 'target.<name>' directory; a missing directory is a CheckpointError, not a KeyError."""
+  import msgpack
+  from music_spectrogram_diffusion_b200 import t5x_checkpoint as X
+  params = {'decoder/decoder_norm/scale': np.arange(8, dtype=np.float32),
+            'decoder/spec_out_dense/kernel': np.arange(32, dtype=np.float32).reshape(8, 4)}
+  ck = X.save_t5x_checkpoint(str(tmp_path / 'checkpoint_7'), params, step=7)
+  idx = os.path.join(ck, 'checkpoint')
+  state = msgpack.unpackb(open(idx, 'rb').read(), ext_hook=X._ext_hook, raw=False, strict_map_key=False)
+
+  def rewrite(node):
+    for k, v in list(node.items()):
+      if isinstance(v, dict) and v.get('driver') == 'zarr':
+        path = v['kvstore']['path']
+        v['kvstore'] = {'driver': 'gcs', 'bucket': 't5x-dummy-bucket'}
+        if 'scale' in k:
+          v['path'] = path          # gcs form: top-level path
+        # the kernel keeps no path at all -> 'target.<name>' fallback
+      elif isinstance(v, dict):
+        rewrite(v)
+  rewrite(state)
+  # an inline chunked array with flax's dict-shaped 'shape'
+  tgt = X._target_tree(state)
+  tgt['extra'] = {X._CHUNK_MARK: True, 'shape': {'0': 2, '1': 3},
+                  'chunks': {'0': np.arange(4, dtype=np.float32), '1': np.arange(4, 6, dtype=np.float32)}}
+  open(idx, 'wb').write(msgpack.packb(state, default=X._default, use_bin_type=True))
+  got = X.load_t5x_checkpoint(ck)
+  for k, v in params.items():
+    np.testing.assert_array_equal(got[k], v)
+  np.testing.assert_array_equal(got['extra'], np.arange(6, dtype=np.float32).reshape(2, 3))
+  # remove an array directory: loud CheckpointError
+  import shutil
+  shutil.rmtree(os.path.join(ck, 'target.decoder.spec_out_dense.kernel'))
+  with pytest.raises(X.CheckpointError, match='not found'):
+    X.load_t5x_checkpoint(ck)
