@@ -178,7 +178,7 @@ _ORACLE_PARAMS = {}
 
 def cpu_oracle_sample(t5, diff, lengths, n_steps, threads):
   """Time the oracle port (graph AS WRITTEN) on one segment: encode + n_steps full CFG steps;
-  returns (seconds_encode, seconds_per_step)."""
+  returns (seconds_encode, mean seconds per diffusion step, [seconds of every step])."""
   import torch
   from music_spectrogram_diffusion_b200 import weights
   from oracle import msd_oracle as O
@@ -207,44 +207,65 @@ def cpu_oracle_sample(t5, diff, lengths, n_steps, threads):
       f = 1.0 if cond else 0.0
       return O.decode(params, oc, [(e * f, m * f) for e, m in encs], zz, time_)
 
-    t0 = time.perf_counter()
     i0 = oc.num_steps - 1
+    per_step = []
     for k in range(n_steps):
+      t0 = time.perf_counter()
       z = O.eval_step(z, i0 - k, torch.randn(z.shape, generator=g), pred_fn, oc)
-    t_step = (time.perf_counter() - t0) / n_steps
-  return t_enc, t_step
+      per_step.append(time.perf_counter() - t0)
+  return t_enc, float(np.mean(per_step)), per_step
+
+
+def cpu_sample_text(cores, n_cpu_steps, t_enc, per_step, num_steps, extra=''):
+  """`sample` string of cpu_baseline: says EXTRAPOLATED first, then what was really timed."""
+  return (f'EXTRAPOLATED from a bounded sample: oracle port (torch-CPU fp32, graph as written) on '
+          f'{cores} threads, 1 segment: encode ({t_enc:.2f} s) + {n_cpu_steps} full CFG diffusion '
+          f'steps really timed (mean {np.mean(per_step):.3f} s, min {np.min(per_step):.3f}, max '
+          f'{np.max(per_step):.3f}), value = 256 frames / (encode + {num_steps} x mean step); steps '
+          f'are identical work and segments independent, so frames/s does not depend on the '
+          f'segment count{extra}')
 
 
 def run_reference(args):
   """--impl reference: the reference's own algorithm on the host cores.  The JAX reference is
-  not installable here (no jax/flax/t5x wheels), so this is the oracle port, graph as written."""
+  not installable here (no jax/flax/t5x wheels), so this is the oracle port, graph as written.
+  Each bench "step" is one bounded sample (encode + --cpu-steps diffusion steps of one segment);
+  `ms_per_step` is the measured time of that sample, `value` the frames/s it extrapolates to."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   t5, diff, lengths = model_configs(args)
   cores = best_thread_count(t5, diff, lengths)
   n_cpu_steps = args.cpu_steps
-  times = []
+  num_steps = diff.sampler.schedule.num_steps
+  secs, samples, all_steps, encs = [], [], [], []
   for it in range(args.warmup + args.steps):
-    t_enc, t_step = cpu_oracle_sample(t5, diff, lengths, n_cpu_steps, cores)
-    sec = t_enc + diff.sampler.schedule.num_steps * t_step
+    t0 = time.perf_counter()
+    t_enc, t_step, per_step = cpu_oracle_sample(t5, diff, lengths, n_cpu_steps, cores)
+    wall = time.perf_counter() - t0
     if it >= args.warmup:
-      times.append(sec)
-  sec = float(np.mean(times))
+      secs.append(t_enc + num_steps * t_step)
+      samples.append(wall)
+      all_steps += per_step
+      encs.append(t_enc)
+  sec = float(np.mean(secs))
   value = lengths['targets'] / sec
-  sample = (f'oracle port on {cores} threads; 1 of the {args.segments} segments: encode + '
-            f'{n_cpu_steps} full CFG diffusion steps of the graph as written, extrapolated '
-            f'linearly to {diff.sampler.schedule.num_steps} steps (segments are independent, so '
-            'frames/s does not depend on the segment count)')
+  sample = cpu_sample_text(cores, n_cpu_steps, float(np.mean(encs)), all_steps, num_steps,
+                           f'; {args.steps} such samples after {args.warmup} warm-up samples')
   line = {
       'impl': 'reference', 'metric': 'mel-frames/sec', 'value': value, 'unit': 'frames/s',
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-      'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'ms_per_step': float(np.mean(samples)) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'x_realtime': value / FRAME_RATE,
+      'x_realtime': value / FRAME_RATE, 'extrapolated': True,
+      'extrapolated_seconds_per_segment': sec,
       'config': workload_config(args, t5, lengths, segments=args.segments),
       'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores,
-                       'cores_available': usable_cores(), 'kind': 'port', 'sample': sample},
+                       'cores_available': usable_cores(), 'kind': 'port', 'sample': sample,
+                       'diffusion_steps_timed': len(all_steps),
+                       'seconds_per_diffusion_step': {'mean': float(np.mean(all_steps)),
+                                                      'min': float(np.min(all_steps)),
+                                                      'max': float(np.max(all_steps))}},
       'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
@@ -272,6 +293,116 @@ def peaks():
       j = json.load(f)
     return j.get('bf16_tflops_sustained', 1388.2), j.get('hbm_gbs', 6483.9), 'measured'
   return 1400.0, 6650.0, 'fallback'
+
+
+KERNEL_CLASS_KEYS = ('gemm', 'attention_combine', 'attention', 'rmsnorm', 'sampler')
+
+
+def kernel_class(name: str) -> str:
+  for k in KERNEL_CLASS_KEYS:
+    if k in name:
+      return k
+  return 'other'
+
+
+def graph_timeline(eng, seed=2):
+  """In-graph timeline of ONE replayed diffusion step (CUPTI through torch.profiler): the per-launch
+  CUDA events of `profile_step` serialise the kernels, the replayed graph overlaps every kernel's
+  prologue with its predecessor (programmatic dependent launch).  The critical path of a kernel
+  is the time it adds to the step: own end - latest end seen before it.  Returns (summary, rows)
+  for a step in the middle of an `eng.sample` call, or (None, None) if CUPTI is unavailable."""
+  import tempfile
+  import torch
+  try:
+    for _ in range(2):
+      eng.sample(seed=1)
+    torch.cuda.synchronize()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+      eng.sample(seed=seed)
+      torch.cuda.synchronize()
+    path = os.path.join(tempfile.mkdtemp(), 'trace.json')
+    prof.export_chrome_trace(path)
+    with open(path) as f:
+      ev = [e for e in json.load(f)['traceEvents'] if e.get('cat') == 'kernel']
+  except Exception as e:  # pylint: disable=broad-except
+    return {'unavailable': f'{type(e).__name__}: {e}'}, None
+  ev.sort(key=lambda e: e['ts'])
+  # a step = everything after one sampler_step kernel up to and including the next
+  ends = [i for i, e in enumerate(ev) if 'sampler_step' in e['name']]
+  if len(ends) < 4:
+    return {'unavailable': f'only {len(ends)} steps in the trace'}, None
+  lo, hi = ends[len(ends) // 2 - 1] + 1, ends[len(ends) // 2] + 1
+  step = ev[lo:hi]
+  t0 = step[0]['ts']
+  rows, crit, busy = [], {}, {}
+  prev_end = t0
+  for e in step:
+    c = kernel_class(e['name'])
+    end = e['ts'] + e['dur']
+    add = max(0.0, end - prev_end)
+    rows.append({'kernel': c, 'start_us': round(e['ts'] - t0, 2), 'dur_us': round(e['dur'], 2),
+                 'critical_us': round(add, 2), 'grid': e.get('args', {}).get('grid'),
+                 'block': e.get('args', {}).get('block')})
+    crit[c] = crit.get(c, 0.0) + add
+    busy[c] = busy.get(c, 0.0) + e['dur']
+    prev_end = max(prev_end, end)
+  total = prev_end - t0
+  summary = {'kernels': len(step), 'step_us': round(total, 1),
+             'critical_path_us_by_class': {k: round(v, 1) for k, v in crit.items()},
+             'critical_path_share_by_class': {k: round(v / total, 4) for k, v in crit.items()},
+             'busy_us_by_class': {k: round(v, 1) for k, v in busy.items()},
+             'how': 'CUPTI kernel records of one replayed step graph; critical = own end - latest '
+                    'earlier end'}
+  return summary, rows
+
+
+def measure_gemm_traffic(args, timeout_s=240):
+  """dram__bytes_read + write of the dominant kernel (CTA-pair GEMM), per launch, from an ncu pass
+  over one uncaptured diffusion step of this very workload (tools/profile_step.py in a child
+  process; two metrics = one replay pass).  Returns a dict, or {'unavailable': why}."""
+  import shutil
+  import subprocess
+  import tempfile
+  ncu = shutil.which('ncu') or ('/usr/local/cuda/bin/ncu' if os.path.exists('/usr/local/cuda/bin/ncu') else None)
+  if ncu is None:
+    return {'unavailable': 'ncu not found'}
+  log = os.path.join(tempfile.mkdtemp(), 'traffic.csv')
+  # encode issues 109 GEMM launches for base (2 encoders x 12 layers x 4 + context input
+  # projection + 12 cross K/V), then one warm-up step of 74 and the measured one
+  skip = {'base': 109 + 74}.get(args.model)
+  if skip is None or args.precision != 'bf16':
+    return {'unavailable': 'launch indices are tabulated for the base bf16 workload only'}
+  cmd = [ncu, '--metrics', 'dram__bytes_read.sum,dram__bytes_write.sum', '--clock-control', 'none',
+         '-k', 'regex:gemm_bf16_tcgen05_pair', '-s', str(skip), '-c', '74', '--csv', '--log-file', log,
+         sys.executable, os.path.join(ROOT, 'tools', 'profile_step.py'), '--model', args.model,
+         '--segments', str(args.segments), '--diffusion-steps', str(args.diffusion_steps)]
+  try:
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+  except Exception as e:  # pylint: disable=broad-except
+    return {'unavailable': f'{type(e).__name__}: {e}'}
+  if not os.path.exists(log):
+    return {'unavailable': f'ncu wrote no log (rc {r.returncode}): {r.stderr[-200:]}'}
+  import csv
+  total, ids = 0.0, set()
+  with open(log) as f:
+    lines = [ln for ln in f if not ln.startswith('==')]
+  for row in csv.DictReader(lines):
+    name = row.get('Metric Name', '')
+    if name.startswith('dram__bytes_'):
+      try:
+        v = float(row['Metric Value'].replace(',', ''))
+      except ValueError:
+        continue
+      unit = row.get('Metric Unit', 'byte').lower()
+      v *= {'byte': 1.0, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(unit, 1.0)
+      total += v
+      ids.add(row.get('ID'))
+  if not ids:
+    return {'unavailable': f'no dram__bytes rows in the ncu log (rc {r.returncode}): '
+                           f'{(r.stderr or r.stdout)[-200:]}'}
+  return {'dram_bytes_per_launch': total / len(ids), 'launches': len(ids),
+          'how': 'ncu dram__bytes_read.sum + dram__bytes_write.sum over the 74 CTA-pair GEMM '
+                 'launches of one uncaptured diffusion step, measured in this run'}
 
 
 def single_song_sample(t5, diff, lengths, device_index, segments=3):
@@ -320,7 +451,8 @@ def run_ours(args):
   t5, diff, lengths = model_configs(args)
   B = args.segments
   model = inference.InferenceModel.from_config(
-      t5, diff, lengths, checkpoint_path='synthetic:0', batch_size=B, device=local)
+      t5, diff, lengths, checkpoint_path='synthetic:0', batch_size=B, device=local,
+      precision=args.precision)
   eng = model.engine
   batch = synthetic_batch(B, lengths, seed=100 + rank)
   d_tok = torch.from_numpy(batch['encoder_input_tokens']).to(dev)
@@ -384,16 +516,33 @@ def run_ours(args):
     gemm_tf = g['flops'] / (g['ms'] * 1e-3) / 1e12 if g['ms'] > 0 else 0.0
     a = prof['attention']
     attn_tf = a['flops'] / (a['ms'] * 1e-3) / 1e12 if a['ms'] > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'gemm_traffic.json')
-    if os.path.exists(tpath):
-      with open(tpath) as f:
-        traffic = json.load(f).get('dram_bytes_per_launch')
+    # in-graph critical path (what the replayed graph really spends per kernel class)
+    timeline = None
+    if not args.no_timeline:
+      eng.encode(d_tok, d_ctx, d_msk)
+      timeline, _ = graph_timeline(eng)
+    # DRAM traffic of the dominant kernel, measured in this run when ncu may read the counters
+    traffic, traffic_info = None, {'unavailable': 'skipped (--no-traffic or N > 1)'}
+    if world == 1 and not args.no_traffic:
+      traffic_info = measure_gemm_traffic(args)
+      traffic = traffic_info.get('dram_bytes_per_launch')
+    if traffic is None:
+      tpath = os.path.join(ROOT, 'profiles', 'gemm_traffic.json')
+      if os.path.exists(tpath):
+        with open(tpath) as f:
+          traffic = json.load(f).get('dram_bytes_per_launch')
+        traffic_info = dict(traffic_info, fallback='profiles/gemm_traffic.json (recorded by an '
+                            'earlier ncu --set full capture, not measured in this run)')
+    g_crit = (timeline or {}).get('critical_path_us_by_class', {}).get('gemm')
     roofline = {
         'kernel': 'gemm_bf16_tcgen05_pair_kernel', 'bound': 'tensor',
         'achieved': gemm_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
         'frac': gemm_tf / peak_tf, 'peak_source': f'{peak_kind} (bf16 sustained)',
-        'traffic': traffic,
+        'traffic': traffic, 'traffic_source': traffic_info,
+        'algorithmic_bytes_per_launch': g['bytes'] / max(g['launches'], 1),
+        # the same FLOPs over the time the class adds to the replayed step graph (PDL overlap)
+        'achieved_in_graph': (g['flops'] / (g_crit * 1e-6) / 1e12) if g_crit else None,
+        'frac_in_graph': (g['flops'] / (g_crit * 1e-6) / 1e12 / peak_tf) if g_crit else None,
         'launches_per_diffusion_step': g['launches'],
         'avg_launch_us': 1e3 * g['ms'] / max(g['launches'], 1),
         'share_of_step': g['ms'] / total_ms if total_ms > 0 else None,
@@ -404,7 +553,9 @@ def run_ours(args):
         'metric': 'mel-frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16', 'data': 'synthetic',
+        'dtype': 'bf16' if args.precision == 'bf16' else
+                 'f32 (3 x bf16 split tensor-core products ~2^-16, fp32 attention / softmax / residual)',
+        'data': 'synthetic',
         'x_realtime': value / FRAME_RATE,
         'config': workload_config(args, t5, lengths, B),
         'clocks': clocks,
@@ -423,21 +574,23 @@ def run_ours(args):
             'wall_seconds': wall,
         },
         'kernel_classes_ms_per_diffusion_step': {k: round(v['ms'], 4) for k, v in prof.items()},
+        'in_graph': timeline,
         'attention_tflops': attn_tf,
     }
     if world == 1 and not args.no_song and lengths['inputs'] >= 2048:
       line['single_song'] = single_song_sample(t5, diff, lengths, local)
     if world == 1 and not args.no_cpu_baseline:
       cores = best_thread_count(t5, diff, lengths)
-      t_enc, t_step = cpu_oracle_sample(t5, diff, lengths, args.cpu_steps, cores)
+      t_enc, t_step, per_step = cpu_oracle_sample(t5, diff, lengths, args.cpu_steps, cores)
       cpu_sec = t_enc + args.diffusion_steps * t_step
       line['cpu_baseline'] = {
           'value': lengths['targets'] / cpu_sec, 'unit': 'frames/s', 'cores': cores,
-          'cores_available': usable_cores(), 'kind': 'port',
-          'sample': f'oracle (torch-CPU fp32, graph as written, '
-                    f'{as_written_flops(t5, lengths) / 1e9:.1f} GFLOP/step): 1 segment, encode '
-                    f'({t_enc:.2f} s) + {args.cpu_steps} CFG steps ({t_step:.3f} s each), '
-                    f'extrapolated to {args.diffusion_steps} steps',
+          'cores_available': usable_cores(), 'kind': 'port', 'extrapolated': True,
+          'sample': cpu_sample_text(cores, args.cpu_steps, t_enc, per_step, args.diffusion_steps,
+                                    f' ({as_written_flops(t5, lengths) / 1e9:.1f} GFLOP per step)'),
+          'seconds_per_diffusion_step': {'mean': float(np.mean(per_step)),
+                                         'min': float(np.min(per_step)),
+                                         'max': float(np.max(per_step))},
       }
     print(json.dumps(line))
   if world > 1:
@@ -454,8 +607,14 @@ def main():
   ap.add_argument('--model', default='base', choices=['base', 'small', 'tiny'])
   ap.add_argument('--segments', type=int, default=8, help='segments per GPU (B)')
   ap.add_argument('--diffusion-steps', type=int, default=1000)
-  ap.add_argument('--cpu-steps', type=int, default=2,
+  ap.add_argument('--cpu-steps', type=int, default=10,
                   help='diffusion steps in the bounded CPU sample')
+  ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32_accurate'],
+                  help='fp32_accurate: BASELINE config 2 (use with --segments 1)')
+  ap.add_argument('--no-timeline', action='store_true',
+                  help='skip the in-graph (CUPTI) critical-path split per kernel class')
+  ap.add_argument('--no-traffic', action='store_true',
+                  help='skip the ncu DRAM-traffic measurement of the dominant kernel')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-song', action='store_true',
                   help='skip the batch-1 chained-song sample (BASELINE config 5 in miniature)')

@@ -513,8 +513,9 @@ def test_fp32_accurate_decoder_forward(cuda_device, tiny):
                                                    ('ddpm', 1.0, 'concat_encodings'),
                                                    ('ddpm', 2.0, 'sum_cross_attends')])
 def test_fp32_accurate_sample_matches_oracle(cuda_device, sampler, weight, style):
-  """Full trajectories in the fp32-accurate mode: mean |d| <= 1e-3 normalised (SURVEY 8d's fp32
-  tolerance), an order of magnitude inside the bf16 path's 3e-2."""
+  """Full trajectories in the fp32-accurate mode.  SURVEY 8d's fp32 tolerance is mean |d| <= 1e-3
+  normalised; measured on B200: mean 3-5e-6, p99 5e-5, max 3e-4 -- the bounds asserted are ten
+  times the measured values, i.e. 10x inside the stated tolerance."""
   t5 = config.t5_tiny()
   t5.decoder_cross_attend_style = style
   params = weights.synthetic_params(t5, T, N, C, seed=0 if style == 'concat_encodings' else 5)
@@ -531,14 +532,15 @@ def test_fp32_accurate_sample_matches_oracle(cuda_device, sampler, weight, style
                                     init_z, noise)
   err = (mel - ref).abs() / (oc.max_value - oc.min_value) * 2.0
   H.assert_trajectory_close(err, f'fp32-accurate tiny {sampler} w={weight} {style}',
-                            mean=1e-3, p99=1e-2, share_01=2e-3)
+                            mean=1e-4, p99=1e-3, share_01=1e-5)
   eng.close()
 
 
 @pytest.mark.parametrize('steps', [20, 1000])
 def test_fp32_accurate_base_with_context_matches_oracle_fixture(cuda_device, steps):
   """BASELINE config 2 as written: base_with_context, 1 segment, fp32 vs the reference tolerance
-  (mean |d| <= 1e-3 normalised over the full trajectory)."""
+  (mean |d| <= 1e-3 normalised over the full trajectory).  Measured on B200 at 20
+  steps: mean 1.0e-5, p99 1.3e-4, max 6e-4; asserted: 10x those, still 10x inside 1e-3."""
   import os
   import bench
   from music_spectrogram_diffusion_b200 import inference
@@ -563,4 +565,4 @@ def test_fp32_accurate_base_with_context_matches_oracle_fixture(cuda_device, ste
   err = np.abs(mel - g['mel']) / (4.0 - np.log(1e-5)) * 2.0
   assert np.isfinite(mel).all()
   H.assert_trajectory_close(err, f'fp32-accurate base_with_context, 1 segment, {steps} steps',
-                            mean=1e-3, p99=1e-2, share_01=2e-3)
+                            mean=1e-4, p99=1.5e-3, share_01=1e-5)
