@@ -32,6 +32,13 @@ struct AttnF32Dev {
   int heads, Lq, Lk;
   const uint32_t* mask_bits; int mask_stride_words;
   int kv_batch_rows, kv_row0;
+  // split-KV (small grids, e.g. one segment's cross-attention: 96 CTAs): blockIdx.z = batch *
+  // splits + split; each split covers nkb / splits key blocks and leaves an unnormalised partial
+  // (o, m, l) that attention_f32_combine_kernel merges.  More CTAs per SM also hides the
+  // synchronous K/V tile loads.
+  int splits;
+  float* part_o;   // [rows * heads * splits][64]
+  float* part_ml;  // [rows * heads * splits][2]
 };
 
 __global__ void __launch_bounds__(F32_THREADS)
@@ -44,7 +51,9 @@ attention_f32_kernel(const AttnF32Dev p) {
   griddep_launch_dependents();
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;   // tx: key / dim group, ty: row group (4 rows)
-  const int q0 = blockIdx.x * FQ, head = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * FQ, head = blockIdx.y;
+  const int b = static_cast<int>(blockIdx.z) / p.splits;
+  const int split = static_cast<int>(blockIdx.z) - b * p.splits;
   const uint32_t* mrow =
       p.mask_bits ? p.mask_bits + static_cast<size_t>(b) * p.mask_stride_words : nullptr;
   griddep_wait();
@@ -68,8 +77,9 @@ attention_f32_kernel(const AttnF32Dev p) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) o[r][c] = 0.f;
   }
-  const int nkb = p.Lk / FK;
-  for (int j = 0; j < nkb; ++j) {
+  const int nkb_all = p.Lk / FK;
+  const int kb0 = split * nkb_all / p.splits, nkb = (split + 1) * nkb_all / p.splits;
+  for (int j = kb0; j < nkb; ++j) {
     uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
     if (mrow != nullptr) {
       w0 = mrow[2 * j];
@@ -169,6 +179,17 @@ attention_f32_kernel(const AttnF32Dev p) {
       }
     }
   }
+  if (p.splits > 1) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const size_t prow =
+          (static_cast<size_t>(b * p.Lq + q0 + ty * 4 + r) * p.heads + head) * p.splits + split;
+      *reinterpret_cast<float4*>(p.part_o + prow * FD + tx * 4) =
+          make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
+      if (tx == 0) *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m[r], l[r]);
+    }
+    return;
+  }
   // normalise and write [hi | lo | hi]; thread: rows ty*4 + r, dims tx*4 .. +3 (8 bytes each)
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -187,6 +208,45 @@ attention_f32_kernel(const AttnF32Dev p) {
     *reinterpret_cast<uint2*>(orow + p.o_third) = ul;
     *reinterpret_cast<uint2*>(orow + 2 * p.o_third) = uh;
   }
+}
+
+// out = sum_s w_s O_s / sum_s w_s l_s, w_s = exp(m_s - max_s m_s), written as [hi | lo | hi]
+__global__ void __launch_bounds__(256)
+attention_f32_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                             bf16* __restrict__ O, int o_third, int heads, int splits,
+                             long long n_rh) {
+  griddep_launch_dependents();
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long rh = gid >> 4;  // (row, head) pair; 16 threads x 4 columns each
+  const int c4 = static_cast<int>(gid & 15);
+  if (rh >= n_rh) return;
+  griddep_wait();
+  float mmax = -INFINITY;
+  for (int s = 0; s < splits; ++s) mmax = fmaxf(mmax, part_ml[(rh * splits + s) * 2]);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float lt = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float2 ml = *reinterpret_cast<const float2*>(part_ml + (rh * splits + s) * 2);
+    const float w = (ml.x == -INFINITY) ? 0.f : expf(ml.x - mmax);
+    const float4 v = *reinterpret_cast<const float4*>(part_o + (rh * splits + s) * FD + c4 * 4);
+    acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
+    lt += w * ml.y;
+  }
+  const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+  float lo[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    acc[c] *= inv;
+    lo[c] = acc[c] - __bfloat162float(__float2bfloat16_rn(acc[c]));
+  }
+  const long long row = rh / heads;
+  const int head = static_cast<int>(rh - row * heads);
+  const uint2 uh = make_uint2(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]));
+  const uint2 ul = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+  bf16* orow = O + row * (3LL * o_third) + head * FD + c4 * 4;
+  *reinterpret_cast<uint2*>(orow) = uh;
+  *reinterpret_cast<uint2*>(orow + o_third) = ul;
+  *reinterpret_cast<uint2*>(orow + 2 * o_third) = uh;
 }
 
 }  // namespace
@@ -211,11 +271,37 @@ int launch_attention_f32(const AttnF32Args& a, cudaStream_t stream) {
   d.O = a.O; d.o_third = a.o_third; d.heads = a.heads; d.Lq = a.Lq; d.Lk = a.Lk;
   d.mask_bits = a.mask_bits; d.mask_stride_words = a.mask_stride_words;
   d.kv_batch_rows = kv_batch_rows; d.kv_row0 = a.kv_row0;
+  // split the keys when the grid would leave SMs idle (one segment's cross-attention)
+  int splits = 1;
+  const int ctas = (a.Lq / FQ) * a.heads * a.nbatch, nkb = a.Lk / FK;
+  if (a.part_o != nullptr && a.part_ml != nullptr) {
+    if (a.splits > 0) {
+      splits = a.splits;
+    } else {
+      int sms = 148, dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess)
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      for (int s = 2; s <= a.max_splits && ctas * (s - 1) < 3 * sms; ++s)
+        if (nkb % s == 0 && nkb / s >= 4) splits = s;
+    }
+    if (splits > a.max_splits) splits = a.max_splits > 0 ? a.max_splits : 1;
+  }
+  MSD_REQUIRE(nkb % splits == 0, "attention_f32: %d key blocks not divisible by %d splits", nkb, splits);
+  d.splits = splits; d.part_o = a.part_o; d.part_ml = a.part_ml;
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * FD,
                  4.0 * a.nbatch * a.heads * FD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
-  MSD_CUDA_CHECK(launch_kernel(attention_f32_kernel, dim3(a.Lq / FQ, a.heads, a.nbatch),
+  MSD_CUDA_CHECK(launch_kernel(attention_f32_kernel, dim3(a.Lq / FQ, a.heads, a.nbatch * splits),
                                dim3(F32_THREADS), F32_SMEM, stream, d));
   ++g_launch_count;
+  if (splits > 1) {
+    const long long n_rh = static_cast<long long>(a.nbatch) * a.Lq * a.heads;
+    MSD_CUDA_CHECK(launch_kernel(attention_f32_combine_kernel,
+                                 dim3(static_cast<unsigned>((n_rh * 16 + 255) / 256)), dim3(256), 0,
+                                 stream, static_cast<const float*>(a.part_o),
+                                 static_cast<const float*>(a.part_ml), a.O, a.o_third, a.heads,
+                                 splits, n_rh));
+    ++g_launch_count;
+  }
   return 0;
 }
 

@@ -422,14 +422,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           exp_chunk(2, e[0]);
           finish_chunk(1, e[1]);
           exp_chunk(3, e[1]);
+          // the last MUFU of this block has been issued: hand the SFU to the other tile now, its
+          // exps overlap the two remaining finish chunks (adds / packs) and the P store below
+          // (the very last hand-over has no taker and is skipped)
+          if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
           finish_chunk(2, e[0]);
           finish_chunk(3, e[1]);
         };
         if ((mw[0] & mw[1] & mw[2] & mw[3]) == 0xffffffffu) exp_phase(std::false_type{});
         else exp_phase(std::true_type{});
         if (tr) trp[5] = clock64();
-        // hand the SFU to the other tile (the very last hand-over has no taker and is skipped)
-        if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
         float lsum, lsum_hi, lsum2, lsum2_hi;
         unpack2(acc2, lsum, lsum_hi);
         unpack2(acc2b, lsum2, lsum2_hi);

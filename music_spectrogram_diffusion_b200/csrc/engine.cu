@@ -672,6 +672,7 @@ static int attention(const msd_ctx* c, const void* Q, size_t qoff, int ldq, cons
     a.O = O + o_col; a.o_third = o_width;
     a.nbatch = nb; a.heads = H; a.Lq = Lq; a.Lk = Lk; a.mask_bits = bits;
     a.mask_stride_words = stride_words; a.kv_batch_rows = x.kv_batch_rows; a.kv_row0 = x.kv_row0;
+    a.part_o = x.part_o; a.part_ml = x.part_ml; a.max_splits = 8;
     return launch_attention_f32(a, st);
   }
   AttnArgs a;
@@ -1301,7 +1302,8 @@ int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t va
   memset(&ga, 0, sizeof(ga));
   ga.A = a; ga.B = b; ga.M = M; ga.N = N; ga.K = K; ga.lda = K; ga.ldb = K;
   ga.epilogue = epilogue; ga.out = o; ga.ldo = (epilogue == EPI_GATED_GELU) ? N / 2 : N;
-  ga.resid = r; ga.variant = variant; ga.block_n = block_n;
+  ga.resid = (variant == 1) ? r : o;  // CTA-pair kernel: in place (TMA reduce-add), like the engine
+  ga.variant = variant; ga.block_n = block_n;
   cudaStream_t st = nullptr;
   MSD_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   cudaEvent_t e0, e1;
@@ -1479,6 +1481,14 @@ int msd_op_attention_f32(const float* q, const float* k, const float* v, const i
   aa.Q = q; aa.ldq = w; aa.K = k; aa.ldk = w; aa.V = v; aa.ldv = w; aa.O = ob; aa.o_third = w;
   aa.nbatch = nb; aa.heads = heads; aa.Lq = Lq; aa.Lk = Lk; aa.mask_bits = bits;
   aa.mask_stride_words = Lk / 32;
+  float *po = nullptr, *pml = nullptr;
+  MSD_TRY(tb.get(&po, static_cast<size_t>(nb) * Lq * heads * 8 * 64));
+  MSD_TRY(tb.get(&pml, static_cast<size_t>(nb) * Lq * heads * 8 * 2));
+  aa.part_o = po; aa.part_ml = pml; aa.max_splits = 8;
+  {
+    const char* f = getenv("MSD_ATTN_SPLITS");  // test hook: force a split count
+    aa.splits = f ? atoi(f) : 0;
+  }
   MSD_TRY(launch_attention_f32(aa, st));
   MSD_TRY(launch_bf16_rows_to_f32(ob, 3 * w, w, out, static_cast<long long>(nb) * Lq, w, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));

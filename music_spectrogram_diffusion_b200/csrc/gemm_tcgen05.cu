@@ -242,8 +242,8 @@ struct PairCfg {
   static constexpr int HALF_N = BN / 2;
   static constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // epilogue staging: O ring 2 x [128 rows x 128 B] (TMA-store source; the bf16 path uses it as
-  // 4 per-warp transpose tiles) + R ring 2 x [128 x 128 B] (TMA-loaded residual chunks)
+  // epilogue staging: O ring 4 x [128 rows x 128 B] (source of the TMA stores / TMA reduce-adds;
+  // the bf16 path uses the first slot as 4 per-warp transpose tiles)
   static constexpr int EPI_BYTES = 4 * 16384;
   static constexpr int STAGES = (160 * 1024) / STAGE_BYTES > 8 ? 8 : (160 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES =
@@ -337,8 +337,7 @@ template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               const __grid_constant__ CUtensorMap tmap_b,
-                              const __grid_constant__ CUtensorMap tmap_out,
-                              const __grid_constant__ CUtensorMap tmap_res, const GemmDev p) {
+                              const __grid_constant__ CUtensorMap tmap_out, const GemmDev p) {
   using Cfg = PairCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -346,13 +345,12 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* sEpi = sB + STAGES * Cfg::B_STAGE_BYTES;  // O ring [2][16 KB] then R ring [2][16 KB]
+  uint8_t* sEpi = sB + STAGES * Cfg::B_STAGE_BYTES;  // O ring [4][16 KB]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2] (leader's copy is the one used)
-  uint64_t* resid_full_bar = tmem_empty_bar + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_full_bar + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -375,14 +373,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
-      mbar_init(&resid_full_bar[a], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2 && lane == 0 && !epi_is_bf16_out(p.epilogue)) {
-    tma_prefetch_desc(&tmap_out);
-    if (p.epilogue == EPI_RESID_F32) tma_prefetch_desc(&tmap_res);
-  }
+  if (warp == 2 && lane == 0 && !epi_is_bf16_out(p.epilogue)) tma_prefetch_desc(&tmap_out);
   if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before_sync();
   cluster_sync_all();
@@ -452,12 +446,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ---------------- epilogue: 4 warps, TMEM lane group = warp % 4 ----------------
     const int lg = warp & 3;
     uint8_t* tile_smem = sEpi + lg * 4096;
-    uint8_t* sO = sEpi;               // [2][16 KB]
-    uint8_t* sR = sEpi + 2 * 16384;   // [2][16 KB]
+    uint8_t* sO = sEpi;               // [4][16 KB]
     const bool has_res = p.epilogue == EPI_RESID_F32;
     const bool epi_leader = (warp == 2 && lane == 0);
     constexpr int NCH = BN / 32;
-    uint32_t gc = 0;  // running fp32 chunk counter (ring slot = gc & 1, phase = (gc >> 1) & 1)
+    uint32_t gc = 0;  // running fp32 chunk counter (ring slot = gc & 3)
     int tcount = 0;
     griddep_wait();  // residual reads / output writes come after the predecessor is complete
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
@@ -466,15 +459,6 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int tile_row = (tile % m_pairs) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
       const int row0 = tile_row + lg * 32;
       const int n0 = (tile / m_pairs) * BN;
-      if (has_res && epi_leader) {
-        // residual chunks 0 and 1 of this tile travel while the main loop is still running
-#pragma unroll
-        for (int c = 0; c < 2 && c < NCH; ++c) {
-          const uint32_t g = gc + c;
-          mbar_arrive_expect_tx(&resid_full_bar[g & 1], 16384);
-          tma_load_2d(sR + (g & 1) * 16384, &tmap_res, &resid_full_bar[g & 1], n0 + c * 32, tile_row);
-        }
-      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
@@ -550,27 +534,22 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           epilogue_bf16_rows<8>(p, tile_smem, lane, row0, n0 + c, ch);
         }
       } else {
-        // fp32 outputs: registers (+ TMA-loaded residual / position rows) -> swizzled smem tile
-        // -> one TMA store per 128 x 32 chunk.  One named barrier per chunk.
+        // fp32 outputs: registers (+ position rows) -> swizzled smem tile -> one TMA store per
+        // 128 x 32 chunk; the residual form (out == resid: x += acc, the only way the engine uses
+        // it) is a TMA REDUCE-ADD straight into the residual stream, so the residual is never
+        // loaded: no load latency in the epilogue and half its memory traffic.  Four smem slots:
+        // the store of chunk c - 4 must have read its slot before chunk c overwrites it.
         const int trow = lg * 32 + lane;   // row inside the CTA's 128-row tile
         const int grow = tile_row + trow;  // global row
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c, ++gc) {
-          const uint32_t slot = gc & 1;
+          const uint32_t slot = gc & 3;
           tmem_ld_32x32b_x32(t_row + c * 32, r);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (has_res) {
-            mbar_wait(&resid_full_bar[slot], (gc >> 1) & 1);
-            const uint8_t* rrow = sR + slot * 16384 + trow * 128;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 f = *reinterpret_cast<const float4*>(rrow + ((q ^ (trow & 7)) * 16));
-              v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
-            }
-          } else if (p.epilogue == EPI_POS_F32 && grow < p.M) {
+          if (p.epilogue == EPI_POS_F32 && grow < p.M) {
             const int seq = grow / p.pos_rows;
             int pr = grow - seq * p.pos_rows;
             if (p.pos_shift != nullptr) {
@@ -591,21 +570,21 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
             *reinterpret_cast<float4*>(orow + ((q ^ (trow & 7)) * 16)) =
                 make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           fence_proxy_async_smem();
-          // the store that last read the OTHER O slot must be done before anyone rewrites it
-          if (epi_leader) tma_store_wait_read<0>();
+          // after this barrier everyone may write the NEXT chunk's slot: its previous user is the
+          // store issued three chunks ago, so at most the two newest groups may still be reading
+          if (epi_leader) tma_store_wait_read<2>();
           named_barrier_sync(1, 128);
           if (epi_leader) {
             if (tile_row < p.M) {  // M % 128 == 0: a CTA's rows are all valid or all padding
-              tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row);
-              if (p.epilogue == EPI_POS_F32 && p.dup_rows > 0)
-                tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row + p.dup_rows);
+              if (has_res) {
+                tma_reduce_add_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row);
+              } else {
+                tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row);
+                if (p.epilogue == EPI_POS_F32 && p.dup_rows > 0)
+                  tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row + p.dup_rows);
+              }
             }
             tma_store_commit();
-            if (has_res && c + 2 < NCH) {
-              mbar_arrive_expect_tx(&resid_full_bar[slot], 16384);
-              tma_load_2d(sR + slot * 16384, &tmap_res, &resid_full_bar[slot], n0 + (c + 2) * 32,
-                          tile_row);
-            }
           }
         }
       }
@@ -640,7 +619,7 @@ static int gemm_sm_count() {
 
 template <int BN>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                const CUtensorMap& tres, const GemmDev& d, cudaStream_t st) {
+                const GemmDev& d, cudaStream_t st) {
   using Cfg = PairCfg<BN>;
   const int m_pairs = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_tiles = m_pairs * (d.N / BN);
@@ -650,7 +629,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
                  2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
                      4.0 * d.M * d.N, st);
   MSD_CUDA_CHECK(launch_kernel(gemm_bf16_tcgen05_pair_kernel<BN>, dim3(2 * clusters), dim3(192),
-                               Cfg::SMEM_BYTES, st, ta, tb, tout, tres, d));
+                               Cfg::SMEM_BYTES, st, ta, tb, tout, d));
   ++g_launch_count;
   return 0;
 }
@@ -767,19 +746,22 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.resid = a.resid; d.pos = a.pos; d.pos_rows = a.pos_rows > 0 ? a.pos_rows : 1;
   d.pos_shift = a.pos_shift; d.dup_rows = a.dup_rows;
   if (pair) {
-    CUtensorMap tout = ta, tres = ta;  // placeholders unless the epilogue is an fp32 one
+    CUtensorMap tout = ta;  // placeholder unless the epilogue is an fp32 one
     if (!epi_is_bf16_out(a.epilogue)) {
       const int rows = a.M + (a.epilogue == EPI_POS_F32 ? a.dup_rows : 0);
       if (int rc = make_tmap_f32_2d(&tout, a.out, rows, a.N, a.ldo, BLOCK_M)) return rc;
-      if (a.epilogue == EPI_RESID_F32)
-        if (int rc = make_tmap_f32_2d(&tres, a.resid, a.M, a.N, a.ldo, BLOCK_M)) return rc;
+      // the residual epilogue adds into `out` with a TMA reduction: out must already hold resid
+      if (a.epilogue == EPI_RESID_F32 && a.resid != a.out)
+        MSD_CUDA_CHECK(cudaMemcpy2DAsync(a.out, static_cast<size_t>(a.ldo) * 4, a.resid,
+                                         static_cast<size_t>(a.ldo) * 4, static_cast<size_t>(a.N) * 4,
+                                         a.M, cudaMemcpyDeviceToDevice, stream));
     }
     switch (bn) {
-      case 64: return launch_pair<64>(ta, tb, tout, tres, d, stream);
-      case 96: return launch_pair<96>(ta, tb, tout, tres, d, stream);
-      case 128: return launch_pair<128>(ta, tb, tout, tres, d, stream);
-      case 192: return launch_pair<192>(ta, tb, tout, tres, d, stream);
-      default: return launch_pair<256>(ta, tb, tout, tres, d, stream);
+      case 64: return launch_pair<64>(ta, tb, tout, d, stream);
+      case 96: return launch_pair<96>(ta, tb, tout, d, stream);
+      case 128: return launch_pair<128>(ta, tb, tout, d, stream);
+      case 192: return launch_pair<192>(ta, tb, tout, d, stream);
+      default: return launch_pair<256>(ta, tb, tout, d, stream);
     }
   }
   switch (bn) {

@@ -229,6 +229,9 @@ struct AttnF32Args {
   int nbatch, heads, Lq, Lk;
   const uint32_t* mask_bits; int mask_stride_words;
   int kv_batch_rows, kv_row0;  // as in AttnArgs
+  // optional split-KV workspace as in AttnArgs (part_o [rows*heads*max_splits*64] f32, part_ml
+  // [..*2]); splits 0 = automatic (small grids only)
+  float* part_o; float* part_ml; int splits; int max_splits;
 };
 int launch_attention_f32(const AttnF32Args& a, cudaStream_t stream);
 

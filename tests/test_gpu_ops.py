@@ -227,13 +227,19 @@ def test_epilogue_gated_gelu_split_precision(cuda_device, M, F, K):
   assert err < 3e-4 * max(1.0, want.abs().max().item()), err
 
 
+@pytest.mark.parametrize('splits', [0, 1, 3])
 @pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
     (1, 1, 128, 128, False), (2, 3, 256, 384, True), (1, 2, 256, 2304, True),
     (3, 2, 128, 256, True), (2, 12, 256, 256, False)])
-def test_dot_product_attention_fp32(cuda_device, nb, heads, Lq, Lk, masked):
+def test_dot_product_attention_fp32(cuda_device, monkeypatch, nb, heads, Lq, Lk, masked, splits):
   """The fp32 attention of the fp32-accurate mode against the oracle on UNROUNDED fp32 inputs,
-  large logits included (no 1/sqrt(d) scaling in this model)."""
+  large logits included (no 1/sqrt(d) scaling in this model).  splits: 0 = automatic split-KV
+  choice, 1 = single pass, 3 = forced 3-way split + combine."""
   from music_spectrogram_diffusion_b200 import engine
+  if splits == 3 and (Lk // 64) % 3:
+    pytest.skip('key blocks not divisible by 3')
+  if splits:
+    monkeypatch.setenv('MSD_ATTN_SPLITS', str(splits))
   g = torch.Generator().manual_seed(nb * 31 + Lk)
   w = heads * 64
   q = torch.randn(nb, Lq, w, generator=g) * 0.7

@@ -5,17 +5,17 @@ import torch
 from music_spectrogram_diffusion_b200 import _native
 lib = _native.load()
 dev = torch.device('cuda', 0)
-nb, H, Lq, Lk = 8, 12, 256, int(os.environ.get('LK', '2304'))
+nb, H, Lq, Lk = int(os.environ.get('NB', '8')), 12, int(os.environ.get('LQ', '256')), int(os.environ.get('LK', '2304'))
 w = H * 64
 q = torch.randn(nb, Lq, w, device=dev) * 0.3
 k = torch.randn(nb, Lk, w, device=dev) * 0.3
 v = torch.randn(nb, Lk, w, device=dev)
-mask = torch.ones(nb, Lk, dtype=torch.int32, device=dev)
+mask = torch.ones(nb, Lk, dtype=torch.int32, device=dev) if os.environ.get('MASK', '1') == '1' else None
 out = torch.empty_like(q)
 trace = torch.zeros(2 * 64 * 8 + 8, dtype=torch.int64, device=dev)
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 for _ in range(2):
-  rc = lib.msd_op_attention_trace(P(q), P(k), P(v), P(mask), nb, H, Lq, Lk, P(out), P(trace), None)
+  rc = lib.msd_op_attention_trace(P(q), P(k), P(v), P(mask) if mask is not None else None, nb, H, Lq, Lk, P(out), P(trace), None)
   assert rc == 0, lib.msd_last_error()
 torch.cuda.synchronize()
 tt = trace.cpu()
