@@ -18,6 +18,8 @@
 //                       rescaled in TMEM with tcgen05.ld/st), exact because the final division
 //                       uses the same reference max for numerator and denominator
 // Key blocks whose 128 mask bits are all zero are skipped by every role.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -28,16 +30,31 @@ namespace msd {
 namespace {
 
 constexpr int BQ = 128;   // queries per tile
-constexpr int BKV = 128;  // keys per block
 constexpr int HD = 64;    // head dim
 constexpr int Q_BYTES = BQ * HD * 2;         // 16 KB per tile
-constexpr int KV_TILE_BYTES = BKV * HD * 2;  // 16 KB
-constexpr int KV_STAGES = 3;
-constexpr int P_BYTES = BQ * BKV * 2;  // 32 KB per tile (two [128 x 64] swizzled sub-tiles)
-constexpr int ATTN_SMEM = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES + 256 + 1024;
-constexpr uint32_t ATTN_TMEM_COLS = 512;  // S0 [0,128) S1 [128,256) PV0 [256,320) PV1 [320,384)
 constexpr int ATTN_THREADS = 384;  // warps 0-3 / 4-7 softmax tile 0 / 1, 8 TMA, 9 MMA, 10-11 idle
 constexpr float LOG2E = 1.4426950408889634f;
+
+// Two instances, by keys per block:
+//   BKV 128: one CTA per SM (193 KB of shared memory, 384 TMEM columns); two query tiles in flight
+//            per SM.  The per-tile chain of a key block (S wait, TMEM load, max, exp, P store: ~3150
+//            cycles, clock64 trace in profiles/) runs strictly in sequence, so with two tiles the SFU
+//            is busy ~65 % and the issue slots ~26 %: latency-bound.
+//   BKV 64:  half-size K/V stages and P tiles, 256 TMEM columns, 104 registers per softmax thread:
+//            TWO CTAs per SM, i.e. four query tiles in flight per SM, whose phases interleave on
+//            the sub-partitions; grids of up to 2 x SMs CTAs run as a single wave (B = 8
+//            self-attention: 192 CTAs).
+template <int BKV>
+struct ACfg {
+  static constexpr int KV_TILE_BYTES = BKV * HD * 2;   // 16 / 8 KB
+  static constexpr int KV_STAGES = 3;
+  static constexpr int P_BYTES = BQ * BKV * 2;         // 32 / 16 KB per tile ([128 x 64] sub-tiles)
+  static constexpr int NCH = BKV / 32;                 // 32-column chunks of a logits row
+  static constexpr int WPB = BKV / 32;                 // mask words per key block
+  static constexpr uint32_t TMEM_COLS = BKV == 128 ? 512 : 256;  // S0 S1 (BKV each) PV0 PV1 (64 each)
+  static constexpr int SMEM = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES + 256;
+  static constexpr int MIN_CTAS = BKV == 128 ? 1 : 2;
+};
 
 struct AttnDev {
   bf16* O;
@@ -46,19 +63,23 @@ struct AttnDev {
   const uint32_t* mask_bits;
   int mask_stride_words;
   long long* trace;  // optional [2 tiles][64 blocks][8] clock64 stamps of CTA (0,0,0), else null
-  // split-KV: blockIdx.z = batch * splits + split; each split covers nkb / splits key blocks and
-  // writes an unnormalised partial (O fp32, reference max m, sum l) that a combine kernel merges.
-  int splits;
-  float* part_o;   // [rows * heads * splits][64]
-  float* part_ml;  // [rows * heads * splits][2]
-  // tail mode (splits == 1, tail > 0): blockIdx.z = role * nbatch + batch.  Role 1 ("short") CTAs
-  // cover the last `tail` key blocks and publish an unnormalised partial per softmax warp; role 0
-  // ("long") CTAs cover the rest, are scheduled first (lower block index), and merge the partial of
-  // their short partner before the final store.  Balances grids that fill 50-100 % of the SMs.
+  // split-KV: blockIdx.z = batch * splits + split; each split covers nkb / splits key blocks.
+  //   merge == 0: every split writes an unnormalised partial (O fp32, reference max m, sum l) that
+  //               the combine kernel merges;
+  //   merge == 1: splits 1.. publish their partial per softmax warp and raise a flag, split 0 (the
+  //               owner) merges them into its own result before the final store -- no second kernel.
+  //               All CTAs of the grid must be co-resident (the launcher checks).
+  int splits, merge;
+  float* part_o;   // merge 0: [rows * heads * splits][64]; merge 1: per-warp slots, see below
+  float* part_ml;  // merge 0: [rows * heads * splits][2]
+  // tail mode (BKV 128, splits == 1, tail > 0): blockIdx.z = role * nbatch + batch.  Role 1
+  // ("short") CTAs cover the last `tail` key blocks and publish an unnormalised partial per softmax
+  // warp; role 0 ("long") CTAs cover the rest, are scheduled first (lower block index), and merge
+  // the partial of their short partner before the final store.
   int tail, nbatch;
   int kv_static;    // K, V and mask_bits are not produced by the preceding kernels (see TMA warp)
-  int kv_batch_rows, kv_row0;  // K/V row of (batch b, key block j) = b*kv_batch_rows + kv_row0 + j*128
-  uint32_t* flags;  // [nbatch * heads * q-tiles * 4] one per softmax warp, 0 outside a launch
+  int kv_batch_rows, kv_row0;  // K/V row of (batch b, key block j) = b*kv_batch_rows + kv_row0 + j*BKV
+  uint32_t* flags;  // one per (softmax warp, partner), 0 outside a launch
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -72,6 +93,7 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
 
 // Bit j = key block j has at least one attendable key.  One coalesced pass by a whole warp
 // (a serial loop of dependent global loads cost ~3000 cycles per CTA for 18 blocks).
+template <int WPB>
 __device__ __forceinline__ uint64_t active_blocks(const uint32_t* mrow, int nkb_all, int lane) {
   if (mrow == nullptr) return ~0ull;
   uint32_t word[2];
@@ -80,8 +102,13 @@ __device__ __forceinline__ uint64_t active_blocks(const uint32_t* mrow, int nkb_
     const int j = h * 32 + lane;
     bool a = false;
     if (j < nkb_all) {
-      const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
-      a = (w.x | w.y | w.z | w.w) != 0u;
+      if (WPB == 4) {
+        const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
+        a = (w.x | w.y | w.z | w.w) != 0u;
+      } else {
+        const uint2 w = *reinterpret_cast<const uint2*>(mrow + j * 2);
+        a = (w.x | w.y) != 0u;
+      }
     }
     word[h] = __ballot_sync(0xffffffffu, a);
   }
@@ -125,21 +152,29 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+// Per-warp partial slot of the in-kernel merges: [16 float4][32 lanes] of O (512-byte coalesced
+// stores / loads) followed by [32 lanes] float2 (m, l).
+constexpr int SLOT_FLOATS = 32 * HD + 64;
+
+template <int BKV>
+__global__ void __launch_bounds__(ATTN_THREADS, ACfg<BKV>::MIN_CTAS)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const AttnDev p) {
-  extern __shared__ uint8_t smem_raw[];
+  using Cfg = ACfg<BKV>;
+  constexpr int KV_STAGES = Cfg::KV_STAGES;
+  constexpr int KV_TILE_BYTES = Cfg::KV_TILE_BYTES;
+  constexpr int P_BYTES = Cfg::P_BYTES;
+  constexpr int NCH = Cfg::NCH;
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const bool ktr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
                    threadIdx.x == 0;
   long long* ktrp = p.trace + 2 * 64 * 8;  // CTA-level stamps: entry, setup done, loop end, stores done
   if (ktr) ktrp[0] = clock64();
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                                   // [2][16 KB]
-  uint8_t* sK = sQ + 2 * Q_BYTES;                       // [KV_STAGES][16 KB]
-  uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES][16 KB]
-  uint8_t* sP = sV + KV_STAGES * KV_TILE_BYTES;         // [2][32 KB]
+  uint8_t* sK = sQ + 2 * Q_BYTES;                       // [KV_STAGES][KV tile]
+  uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES][KV tile]
+  uint8_t* sP = sV + KV_STAGES * KV_TILE_BYTES;         // [2][P tile]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
   uint64_t* q_full = bars;                  // 1
   uint64_t* kv_full = bars + 1;             // [KV_STAGES]
@@ -183,7 +218,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<ATTN_TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -192,13 +227,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   griddep_launch_dependents();
   if (warp >= 8) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (BKV == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
     // kv_static: K, V and the key mask were written long before the preceding kernel (the
     // cross-attention cache of a diffusion step), so the first ring-full of K/V tiles is
     // requested ahead of the dependency wait; only Q comes from the preceding kernel.
     if (!p.kv_static) griddep_wait();
-    const uint64_t act = active_blocks(mrow, nkb_all, lane);
+    const uint64_t act = active_blocks<Cfg::WPB>(mrow, nkb_all, lane);
     if (lane == 0) {
       int it = 0, j = kb0;
       auto load_kv = [&](int jb) {
@@ -224,7 +260,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp == 9) {
     if (!p.kv_static) griddep_wait();  // mask words may come from the previous kernel
-    const uint64_t act = active_blocks(mrow, nkb_all, lane);
+    const uint64_t act = active_blocks<Cfg::WPB>(mrow, nkb_all, lane);
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P K-major, V MN-major
@@ -239,17 +275,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t kb = k_lo + stage * (KV_TILE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_lo(tmem_base + t * 128, qa + k * 2, kb + k * 2, idesc_s, k != 0 ? 1u : 0u);
+          umma_bf16_lo(tmem_base + t * BKV, qa + k * 2, kb + k * 2, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[t]);
       };
-      // PV_t = P_t V : 8 k-steps of 16 keys.  P: sub-tile (k/4) of 16 KB, +32 B per step inside.
-      // V (MN-major): 16 keys = 16 rows of 128 B -> +2048 B per step; 8-key groups 1024 B apart.
+      // PV_t = P_t V : BKV/16 k-steps of 16 keys.  P: sub-tile (k/4) of 16 KB, +32 B per step
+      // inside.  V (MN-major): 16 keys = 16 rows of 128 B -> +2048 B per step; 8-key groups 1024 B
+      // apart.
       auto issue_pv = [&](int t, int stage, uint32_t acc_first) {
         const uint32_t pa = p_lo + t * (P_BYTES >> 4);
         const uint32_t vb = v_lo + stage * (KV_TILE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
-          umma_bf16_lo(tmem_base + 256 + t * 64, pa + (k >> 2) * ((BQ * 128) >> 4) + (k & 3) * 2,
+          umma_bf16_lo(tmem_base + 2 * BKV + t * 64, pa + (k >> 2) * ((BQ * 128) >> 4) + (k & 3) * 2,
                        vb + k * (2048 >> 4), idesc_pv, k != 0 ? 1u : acc_first);
         umma_commit(&pv_full[t]);
       };
@@ -288,20 +325,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   } else {
     // ------------------------- softmax / output warp groups -------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if (BKV == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int tile = warp >> 2;  // 0: warps 0..3, 1: warps 4..7
     if (!p.kv_static) griddep_wait();  // mask words may come from the previous kernel
-    const uint64_t act = active_blocks(mrow, nkb_all, lane);
+    const uint64_t act = active_blocks<Cfg::WPB>(mrow, nkb_all, lane);
     griddep_wait();  // O is written by these warps
     if (tile < nq) {
       const int lg = warp & 3;
       const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
       const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
-      const uint32_t tmem_s = tmem_base + tile * 128 + lane_off;
-      const uint32_t tmem_pv = tmem_base + 256 + tile * 64 + lane_off;
+      const uint32_t tmem_s = tmem_base + tile * BKV + lane_off;
+      const uint32_t tmem_pv = tmem_base + 2 * BKV + tile * 64 + lane_off;
       uint8_t* sPt = sP + tile * P_BYTES;
       float m = -INFINITY, l = 0.f;  // reference max (natural units) and running sum
-      uint32_t s[4][32];
+      uint32_t s[NCH][32];
       // Ping-pong of the SFU-bound exp phase between the two tiles' warpgroups (named barriers
       // 2 + tile: "tile may run its exps"): without it both groups run in lockstep and collide on
       // the SFU while it idles during their max / store / wait phases (ncu: XU 41 % busy).
@@ -313,10 +351,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int it = 0;
       for (int j = kb0; j < nkb; ++j) {
         if (!block_active(act, j)) continue;
-        uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        uint32_t mw[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) mw[c] = 0xffffffffu;
         if (mrow != nullptr) {
-          const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
-          mw[0] = w.x; mw[1] = w.y; mw[2] = w.z; mw[3] = w.w;
+          if (NCH == 4) {
+            const uint4 w = *reinterpret_cast<const uint4*>(mrow + j * 4);
+            mw[0] = w.x; mw[1] = w.y; mw[NCH - 2] = w.z; mw[NCH - 1] = w.w;
+          } else {
+            const uint2 w = *reinterpret_cast<const uint2*>(mrow + j * 2);
+            mw[0] = w.x; mw[1] = w.y;
+          }
         }
         const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 &&
                         blockIdx.z == 0 && lg == 0 && lane == 0 && it < 64;
@@ -326,7 +371,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after_sync();
         if (tr) trp[1] = clock64();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + c * 32, s[c]);
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tmem_s + c * 32, s[c]);
         tmem_ld_wait();
         if (tr) trp[2] = clock64();
         tc_fence_before_sync();
@@ -336,9 +381,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         float mx[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+        bool all_on = true;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           const uint32_t bits = mw[c];
+          all_on = all_on && (bits == 0xffffffffu);
           if (bits == 0xffffffffu) {
 #pragma unroll
             for (int i = 0; i < 32; i += 2)
@@ -361,9 +408,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           mbar_wait(&pv_full[tile], (it - 1) & 1);  // previous PV has landed in O
           tc_fence_after_sync();
           waited_pv = true;
-          uint32_t ob[32];
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < 2; ++c) {
+            uint32_t ob[32];
             tmem_ld_32x32b_x32(tmem_pv + c * 32, ob);
             tmem_ld_wait();
 #pragma unroll
@@ -379,17 +426,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (pingpong) named_barrier_sync(2 + tile, 256);  // my turn on the SFU
         if (tr) trp[4] = clock64();
         // p = exp(s - m) as bf16 pairs (packed in place into s[c][0..15]), row sum in fp32.
-        // Software-pipelined by one 32-column chunk: the SFU exps of chunk c are independent of
-        // the adds / packs of chunk c-1 issued next to them, so the MUFUs go out back to back.
         const uint64_t l2e2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
         uint64_t acc2 = pack2(0.f, 0.f), acc2b = pack2(0.f, 0.f);
+        // the last MUFU of this block has been issued: hand the SFU to the other tile, its exps
+        // overlap the remaining adds / packs and the P store below (the very last hand-over has no
+        // taker and is skipped)
+        auto handover = [&]() {
+          if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
+        };
         // Two copies of the phase behind a warp-uniform branch: with every key of the block
-        // attendable (the common case) no select instructions are issued.  The phase is bound by
-        // the issue rate of the single warp per sub-partition that runs it (ping-pong), i.e. by
-        // its instruction count (measured ~2.5 cycles per instruction), not by the SFU.
+        // attendable (the common case) no select instructions are issued.
         auto exp_phase = [&](auto masked_tag) {
           constexpr bool MASKED = decltype(masked_tag)::value;
-          float e[2][32];
           auto exp_chunk = [&](int c, float (&dst)[32]) {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -416,20 +464,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
             for (int i = 0; i < 32; i += 2) s[c][i >> 1] = pack_bf16(src[i], src[i + 1]);
           };
-          exp_chunk(0, e[0]);
-          exp_chunk(1, e[1]);
-          finish_chunk(0, e[0]);
-          exp_chunk(2, e[0]);
-          finish_chunk(1, e[1]);
-          exp_chunk(3, e[1]);
-          // the last MUFU of this block has been issued: hand the SFU to the other tile now, its
-          // exps overlap the two remaining finish chunks (adds / packs) and the P store below
-          // (the very last hand-over has no taker and is skipped)
-          if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
-          finish_chunk(2, e[0]);
-          finish_chunk(3, e[1]);
+          if constexpr (NCH == 4) {
+            // Software-pipelined by one 32-column chunk: the SFU exps of chunk c are independent of
+            // the adds / packs of chunk c-1 issued next to them, so the MUFUs go out back to back.
+            float e[2][32];
+            exp_chunk(0, e[0]);
+            exp_chunk(1, e[1]);
+            finish_chunk(0, e[0]);
+            exp_chunk(2, e[0]);
+            finish_chunk(1, e[1]);
+            exp_chunk(3, e[1]);
+            handover();
+            finish_chunk(2, e[0]);
+            finish_chunk(3, e[1]);
+          } else {
+            // 104 registers per thread: one 32-wide staging buffer; the second chunk's exps are
+            // issued while the first chunk is summed and packed
+            float e0[32], e1[32];
+            exp_chunk(0, e0);
+            exp_chunk(1, e1);
+            handover();
+            finish_chunk(0, e0);
+            finish_chunk(1, e1);
+          }
         };
-        if ((mw[0] & mw[1] & mw[2] & mw[3]) == 0xffffffffu) exp_phase(std::false_type{});
+        if (all_on) exp_phase(std::false_type{});
         else exp_phase(std::true_type{});
         if (tr) trp[5] = clock64();
         float lsum, lsum_hi, lsum2, lsum2_hi;
@@ -441,7 +500,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (it > 0 && !waited_pv) mbar_wait(&pv_full[tile], (it - 1) & 1);
         if (tr) trp[6] = clock64();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           // columns [c*32, c*32+32) -> sub-tile c/2, 16-byte chunks (c&1)*4 .. +3, XOR row&7
           uint8_t* prow = sPt + (c >> 1) * (BQ * 128) + r * 128;
 #pragma unroll
@@ -458,90 +517,130 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         ++it;
       }
       if (ktr) ktrp[2] = clock64();
-      float o[HD];
       if (it > 0) {
         mbar_wait(&pv_full[tile], (it - 1) & 1);
         tc_fence_after_sync();
-        uint32_t ob[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+      }
+      // ---- output.  The O row (64 fp32) is handled in two halves of 32 columns to keep the
+      // register footprint of this section at ~80.
+      auto load_half = [&](int c, float (&o)[32]) {
+        if (it > 0) {
+          uint32_t ob[32];
           tmem_ld_32x32b_x32(tmem_pv + c * 32, ob);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(ob[i]);
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(ob[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0.f;
         }
-      } else {
+      };
+      const int qtiles = (p.Lq + BQ - 1) / BQ;
+      // per-warp slot index of the in-kernel merges (tail mode / merge mode)
+      const size_t wbase =
+          ((static_cast<size_t>(b) * p.heads + head) * qtiles + qgrp * 2 + tile) * 4 + lg;
+      const bool publisher = (p.tail > 0 && role == 1) || (p.merge && p.splits > 1 && split > 0);
+      const int npartners = p.tail > 0 ? (role == 0 ? 1 : 0)
+                                       : ((p.merge && p.splits > 1 && split == 0) ? p.splits - 1 : 0);
+      if (publisher) {
+        // slot of partner index (split - 1) (tail mode: 0)
+        const size_t wslot = wbase * (p.tail > 0 ? 1 : (p.splits - 1)) + (p.tail > 0 ? 0 : split - 1);
+        float* slot = p.part_o + wslot * SLOT_FLOATS;
+        float4* po = reinterpret_cast<float4*>(slot);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          float o[32];
+          load_half(c, o);
 #pragma unroll
-        for (int i = 0; i < HD; ++i) o[i] = 0.f;
-      }
-      // tail mode: one partial slot per softmax warp, laid out [16 float4][32 lanes] so that both
-      // the short CTA's stores and the long CTA's loads are 512-byte coalesced
-      const size_t wslot =
-          ((static_cast<size_t>(b) * p.heads + head) * ((p.Lq + BQ - 1) / BQ) + qgrp * 2 + tile) * 4 + lg;
-      if (p.tail > 0 && role == 1) {
-        float4* po = reinterpret_cast<float4*>(p.part_o + wslot * (32 * HD));
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          po[q * 32 + lane] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        reinterpret_cast<float2*>(p.part_ml + wslot * 64)[lane] = make_float2(m, l);
+          for (int q = 0; q < 8; ++q)
+            po[(c * 8 + q) * 32 + lane] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+        reinterpret_cast<float2*>(slot + 32 * HD)[lane] = make_float2(m, l);
         __threadfence();
         __syncwarp();
         if (lane == 0) st_release_gpu(p.flags + wslot, 1u);
-      } else if (p.splits > 1) {
+      } else if (p.splits > 1 && !p.merge) {
         const size_t prow =
             (static_cast<size_t>(b * p.Lq + q0 + tile * BQ + r) * p.heads + head) * p.splits + split;
         float4* po = reinterpret_cast<float4*>(p.part_o + prow * HD);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          float o[32];
+          load_half(c, o);
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-          po[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          for (int q = 0; q < 8; ++q)
+            po[c * 8 + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
         *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m, l);
       } else {
-      if (p.tail > 0) {
-        // merge the short partner's partial: O = w_l O_l + w_s O_s, l likewise, w = exp(m - max m)
-        for (uint32_t spins = 0; ld_acquire_gpu(p.flags + wslot) == 0u; ++spins) {
-          __nanosleep(100);
-          if (spins > (1u << 24)) __trap();  // partner never published: fail loudly, do not hang
+        // owner: merge the partners' partials (O = sum_i w_i O_i, l likewise, w_i = exp(m_i - max m))
+        float mm = m;
+        const size_t wslot0 = wbase * (p.tail > 0 ? 1 : (p.splits > 1 ? p.splits - 1 : 1));
+        for (int pi = 0; pi < npartners; ++pi) {
+          const size_t wslot = wslot0 + pi;
+          for (uint32_t spins = 0; ld_acquire_gpu(p.flags + wslot) == 0u; ++spins) {
+            __nanosleep(100);
+            if (spins > (1u << 24)) __trap();  // partner never published: fail loudly, do not hang
+          }
+          const float2 ml =
+              __ldcg(reinterpret_cast<const float2*>(p.part_o + wslot * SLOT_FLOATS + 32 * HD) + lane);
+          mm = fmaxf(mm, ml.x);
         }
-        const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + wslot * 64) + lane);
-        const float mm = fmaxf(m, ml.x);
         const float wl = (m == -INFINITY) ? 0.f : ex2_approx((m - mm) * LOG2E);
-        const float ws = (ml.x == -INFINITY) ? 0.f : ex2_approx((ml.x - mm) * LOG2E);
-        const float4* po = reinterpret_cast<const float4*>(p.part_o + wslot * (32 * HD));
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 v = __ldcg(po + q * 32 + lane);
-          o[4 * q + 0] = o[4 * q + 0] * wl + v.x * ws;
-          o[4 * q + 1] = o[4 * q + 1] * wl + v.y * ws;
-          o[4 * q + 2] = o[4 * q + 2] * wl + v.z * ws;
-          o[4 * q + 3] = o[4 * q + 3] * wl + v.w * ws;
+        float lt = l * wl;
+        for (int pi = 0; pi < npartners; ++pi) {
+          const float2 ml = __ldcg(
+              reinterpret_cast<const float2*>(p.part_o + (wslot0 + pi) * SLOT_FLOATS + 32 * HD) + lane);
+          lt += (ml.x == -INFINITY) ? 0.f : ml.y * ex2_approx((ml.x - mm) * LOG2E);
         }
-        l = l * wl + ml.y * ws;
+        const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+        // Coalesced store: each warp transposes its 32 rows x 128 B through its own 4 KB slice of
+        // the (now idle) P tile, then writes whole 128-byte row segments (8 lanes per row); the
+        // thread-per-row store cost ~3000 cycles per CTA (32 cache lines per instruction).
+        uint8_t* stg = sPt + lg * 4096;
         __syncwarp();
-        if (lane == 0) p.flags[wslot] = 0u;  // re-armed for the next launch (stream ordered)
-      }
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      // Coalesced store: each warp transposes its 32 rows x 128 B through its own 4 KB slice of
-      // the (now idle) P tile, then writes whole 128-byte row segments (8 lanes per row); the
-      // thread-per-row store cost ~3000 cycles per CTA (32 cache lines per instruction).
-      uint8_t* stg = sPt + lg * 4096;
-      __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          float o[32];
+          load_half(c, o);
+          const float wli = wl * inv;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 u;
-        u.x = pack_bf16(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
-        u.y = pack_bf16(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
-        u.z = pack_bf16(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
-        u.w = pack_bf16(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
-        *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) * 16)) = u;
-      }
-      __syncwarp();
-      bf16* obase = p.O + static_cast<size_t>(b * p.Lq + q0 + tile * BQ + lg * 32) * p.ldo + head * HD;
+          for (int i = 0; i < 32; ++i) o[i] *= wli;
+          for (int pi = 0; pi < npartners; ++pi) {
+            const float* slot = p.part_o + (wslot0 + pi) * SLOT_FLOATS;
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(slot + 32 * HD) + lane);
+            const float ws = (ml.x == -INFINITY) ? 0.f : ex2_approx((ml.x - mm) * LOG2E) * inv;
+            const float4* po = reinterpret_cast<const float4*>(slot);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3), ch = lane & 7;
-        const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) * 16));
-        *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.ldo + ch * 8) = u;
-      }
+            for (int q = 0; q < 8; ++q) {
+              const float4 v = __ldcg(po + (c * 8 + q) * 32 + lane);
+              o[4 * q + 0] = fmaf(v.x, ws, o[4 * q + 0]);
+              o[4 * q + 1] = fmaf(v.y, ws, o[4 * q + 1]);
+              o[4 * q + 2] = fmaf(v.z, ws, o[4 * q + 2]);
+              o[4 * q + 3] = fmaf(v.w, ws, o[4 * q + 3]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16(o[8 * q + 0], o[8 * q + 1]);
+            u.y = pack_bf16(o[8 * q + 2], o[8 * q + 3]);
+            u.z = pack_bf16(o[8 * q + 4], o[8 * q + 5]);
+            u.w = pack_bf16(o[8 * q + 6], o[8 * q + 7]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((c * 4 + q) ^ (lane & 7)) * 16)) = u;
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          for (int pi = 0; pi < npartners; ++pi)
+            p.flags[wslot0 + pi] = 0u;  // re-armed for the next launch (stream ordered)
+        bf16* obase = p.O + static_cast<size_t>(b * p.Lq + q0 + tile * BQ + lg * 32) * p.ldo + head * HD;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+          const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) * 16));
+          *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.ldo + ch * 8) = u;
+        }
       }
       if (ktr) ktrp[3] = clock64();
       tc_fence_before_sync();
@@ -551,7 +650,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (ktr) ktrp[4] = clock64();
   if (warp == 9) {
     tc_fence_after_sync();
-    tmem_dealloc<ATTN_TMEM_COLS>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -591,19 +690,57 @@ attention_combine_kernel(const float* __restrict__ part_o, const float* __restri
 // SMs of the current device (148 on B200).  The long/short split below relies on every short CTA
 // finding an SM that no long CTA occupies, so the real count is used, not the nominal one.
 static int device_sm_count() {
-  static const int sms = [] {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-    return n;
-  }();
-  return sms;
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// CTAs of the 64-key instance that are resident at the same time (2 per SM by construction; the
+// occupancy query also covers a device that grants less, e.g. under an MPS thread limit).
+static int slots_bkv64() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cached_dev) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tcgen05_kernel<64>, ATTN_THREADS,
+                                                      ACfg<64>::SMEM) != cudaSuccess)
+      occ = 0;
+    cached = occ * device_sm_count();
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// Which instance runs: 64-key blocks (2 CTAs per SM) unless MSD_ATTN_BKV=128 asks for the
+// one-CTA-per-SM kernel (kept for comparison and as the fallback when the device grants only one
+// CTA of the small instance per SM).
+static int attention_bkv(int Lk) {
+  const char* e = getenv("MSD_ATTN_BKV");  // read per launch: the tests switch instances
+  const int forced = e ? atoi(e) : 0;
+  if (forced == 128 || forced == 64) return (forced == 64 && Lk % 64 == 0) ? 64 : 128;
+  return (Lk % 64 == 0 && slots_bkv64() >= 2 * device_sm_count()) ? 64 : 128;
 }
 
 int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
-  const int nkb = Lk / BKV;
+  if (attention_bkv(Lk) == 64) {
+    // every CTA of the launch should be resident at once (one wave of 2 CTAs per SM): the largest
+    // split count that fits, with at least four 64-key blocks per CTA
+    const int nkb = Lk / 64, slots = slots_bkv64();
+    int best = 1;
+    for (int s = 2; s <= 12; ++s)
+      if (nkb % s == 0 && nkb / s >= 4 && ctas * s <= slots) best = s;
+    return best;
+  }
+  const int nkb = Lk / 128;
   // measured on B200: splitting pays only when fewer than half the SMs would be busy (B = 8
   // cross-attention, 96 CTAs, is no faster split 3-way: per-CTA fixed costs eat the gain)
   const int sms = device_sm_count();
@@ -616,12 +753,14 @@ int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
   return best;
 }
 
-// Tail split for grids that fill between half and all of the SMs (one CTA per SM): long CTAs take
-// nkb - t key blocks, short CTAs t, shorts run in the SMs the longs leave free (several rounds).
-// Cost model in key-block units with a fixed per-CTA cost F (setup + epilogue, measured ~4.5 on B200: 18 blocks / 96 CTAs -> tail 4).
+// Tail split (128-key instance) for grids that fill between half and all of the SMs (one CTA per
+// SM): long CTAs take nkb - t key blocks, short CTAs t, shorts run in the SMs the longs leave free
+// (several rounds).  Cost model in key-block units with a fixed per-CTA cost F (setup + epilogue,
+// measured ~4.5 on B200: 18 blocks / 96 CTAs -> tail 4).
 int attention_pick_tail(int nbatch, int heads, int Lq, int Lk) {
+  if (attention_bkv(Lk) == 64) return 0;
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
-  const int nkb = Lk / BKV;
+  const int nkb = Lk / 128;
   const int sms = device_sm_count();
   if (ctas < sms / 2 || ctas >= sms || nkb < 6) return 0;
   const int free_sms = sms - ctas;
@@ -638,25 +777,43 @@ int attention_pick_tail(int nbatch, int heads, int Lq, int Lk) {
 }
 
 int attention_configure() {
-  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<128>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128>::SMEM));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<64>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64>::SMEM));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<64>,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_combine_kernel,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   return 0;
 }
 
+// floats of the part_o workspace / flag words a launch may need (engine and op hooks size theirs
+// with these): the larger of the combine-kernel layout and the per-warp slot layout
+size_t attention_workspace_floats(int nbatch, int heads, int Lq, int max_splits) {
+  const size_t rows = static_cast<size_t>(nbatch) * Lq;
+  const size_t combine = rows * heads * max_splits * HD;
+  const size_t warps = static_cast<size_t>(nbatch) * heads * ((Lq + BQ - 1) / BQ) * 4;
+  const size_t slots = warps * (max_splits > 1 ? max_splits - 1 : 1) * SLOT_FLOATS;
+  return combine > slots ? combine : slots;
+}
+size_t attention_flag_words(int nbatch, int heads, int Lq, int max_splits) {
+  return static_cast<size_t>(nbatch) * heads * ((Lq + BQ - 1) / BQ) * 4 * (max_splits > 1 ? max_splits - 1 : 1);
+}
+
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
-  MSD_REQUIRE(a.Lq % BQ == 0 && a.Lk % BKV == 0,
+  static int configured = attention_configure();
+  if (configured != 0) return configured;
+  const int bkv = attention_bkv(a.Lk);
+  MSD_REQUIRE(a.Lq % BQ == 0 && a.Lk % 128 == 0,
               "attention: Lq=%d and Lk=%d must be multiples of 128", a.Lq, a.Lk);
-  MSD_REQUIRE(a.Lk / BKV <= 64, "attention: Lk=%d exceeds 64 key blocks", a.Lk);
+  MSD_REQUIRE(a.Lk / bkv <= 64, "attention: Lk=%d exceeds 64 key blocks", a.Lk);
   MSD_REQUIRE(a.nbatch > 0 && a.heads > 0, "attention: empty problem");
   MSD_REQUIRE(a.ldo % 8 == 0, "attention: ldo must be a multiple of 8");
   if (a.mask_bits)
     MSD_REQUIRE(a.mask_stride_words % 4 == 0 &&
                     (reinterpret_cast<uintptr_t>(a.mask_bits) & 15) == 0,
                 "attention: mask words must be 16-byte aligned per row");
-  static int configured = attention_configure();
-  if (configured != 0) return configured;
   CUtensorMap tq, tk, tv;
   const int width = a.heads * HD;
   if (a.tmap_q) tq = *a.tmap_q;
@@ -667,40 +824,51 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
               kv_batch_rows);
   const uint64_t kv_rows = (uint64_t)a.nbatch * kv_batch_rows;
   if (a.tmap_k) tk = *a.tmap_k;
-  else if (int rc = make_tmap_bf16_2d(&tk, a.K, kv_rows, width, a.ldk, BKV)) return rc;
+  else if (int rc = make_tmap_bf16_2d(&tk, a.K, kv_rows, width, a.ldk, bkv)) return rc;
   if (a.tmap_v) tv = *a.tmap_v;
-  else if (int rc = make_tmap_bf16_2d(&tv, a.V, kv_rows, width, a.ldv, BKV)) return rc;
+  else if (int rc = make_tmap_bf16_2d(&tv, a.V, kv_rows, width, a.ldv, bkv)) return rc;
   AttnDev d;
   d.O = a.O; d.ldo = a.ldo; d.heads = a.heads; d.Lq = a.Lq; d.Lk = a.Lk;
   d.mask_bits = a.mask_bits; d.mask_stride_words = a.mask_stride_words;
   d.trace = a.trace;
+  const int nkb = a.Lk / bkv;
+  const int ctas = ((a.Lq + 2 * BQ - 1) / (2 * BQ)) * a.heads * a.nbatch;
   int splits = (a.part_o != nullptr && a.part_ml != nullptr)
                    ? (a.splits > 0 ? a.splits : attention_pick_splits(a.nbatch, a.heads, a.Lq, a.Lk))
                    : 1;
   if (splits > a.max_splits) splits = a.max_splits > 0 ? a.max_splits : 1;
-  MSD_REQUIRE((a.Lk / BKV) % splits == 0, "attention: %d key blocks not divisible by %d splits",
-              a.Lk / BKV, splits);
+  MSD_REQUIRE(nkb % splits == 0, "attention: %d key blocks not divisible by %d splits", nkb, splits);
   d.splits = splits; d.part_o = a.part_o; d.part_ml = a.part_ml;
+  // In-kernel merge of the splits (no combine kernel): the owner CTAs wait for their partners, so
+  // the whole grid must be resident at once.  MSD_ATTN_MERGE=0 forces the combine kernel.
+  const char* merge_env = getenv("MSD_ATTN_MERGE");
+  const bool merge_allowed = !(merge_env && merge_env[0] == '0');
+  d.merge = (bkv == 64 && splits > 1 && a.flags != nullptr && merge_allowed &&
+             ctas * splits <= slots_bkv64()) ? 1 : 0;
   int tail = 0;
-  if (splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr && a.tail >= 0)
+  if (bkv == 128 && splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr &&
+      a.tail >= 0)
     tail = a.tail > 0 ? a.tail : attention_pick_tail(a.nbatch, a.heads, a.Lq, a.Lk);
-  MSD_REQUIRE(tail < a.Lk / BKV, "attention: tail %d must be below %d key blocks", tail, a.Lk / BKV);
+  MSD_REQUIRE(tail < nkb, "attention: tail %d must be below %d key blocks", tail, nkb);
   if (tail > 0) {
     // long CTAs wait for their short partners: every long CTA must be resident together with at
     // least one SM left for the short ones, or the wait could never end
-    const int longs = ((a.Lq + 2 * BQ - 1) / (2 * BQ)) * a.heads * a.nbatch;
-    MSD_REQUIRE(longs < device_sm_count(), "attention: tail split needs fewer long CTAs (%d) than SMs (%d)",
-                longs, device_sm_count());
+    MSD_REQUIRE(ctas < device_sm_count(), "attention: tail split needs fewer long CTAs (%d) than SMs (%d)",
+                ctas, device_sm_count());
   }
   d.tail = tail; d.nbatch = a.nbatch; d.flags = a.flags; d.kv_static = a.kv_static;
   d.kv_batch_rows = kv_batch_rows; d.kv_row0 = a.kv_row0;
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * (tail > 0 ? 2 : splits));
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
-  MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, stream,
-                               tq, tk, tv, d));
+  if (bkv == 64)
+    MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel<64>, grid, dim3(ATTN_THREADS), ACfg<64>::SMEM,
+                                 stream, tq, tk, tv, d));
+  else
+    MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel<128>, grid, dim3(ATTN_THREADS),
+                                 ACfg<128>::SMEM, stream, tq, tk, tv, d));
   ++g_launch_count;
-  if (splits > 1) {
+  if (splits > 1 && !d.merge) {
     const long long n_rh = static_cast<long long>(a.nbatch) * a.Lq * a.heads;
     const long long threads = n_rh * 16;
     MSD_CUDA_CHECK(launch_kernel(attention_combine_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)),

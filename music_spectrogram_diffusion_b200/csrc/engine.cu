@@ -672,13 +672,13 @@ static int attention(const msd_ctx* c, const void* Q, size_t qoff, int ldq, cons
     a.O = O + o_col; a.o_third = o_width;
     a.nbatch = nb; a.heads = H; a.Lq = Lq; a.Lk = Lk; a.mask_bits = bits;
     a.mask_stride_words = stride_words; a.kv_batch_rows = x.kv_batch_rows; a.kv_row0 = x.kv_row0;
-    a.part_o = x.part_o; a.part_ml = x.part_ml; a.max_splits = 8;
+    a.part_o = x.part_o; a.part_ml = x.part_ml; a.max_splits = 12;
     return launch_attention_f32(a, st);
   }
   AttnArgs a;
   memset(&a, 0, sizeof(a));
   a.kv_static = x.kv_static; a.kv_batch_rows = x.kv_batch_rows; a.kv_row0 = x.kv_row0;
-  a.part_o = x.part_o; a.part_ml = x.part_ml; a.max_splits = 8; a.flags = x.flags;
+  a.part_o = x.part_o; a.part_ml = x.part_ml; a.max_splits = 12; a.flags = x.flags;
   {
     const char* f = getenv("MSD_ATTN_TAIL");  // tuning / test hook: -1 off, 0 auto, n forced
     a.tail = f ? atoi(f) : 0;
@@ -955,9 +955,11 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
     if ((rc = A.alloc(&c->hmid, R * c->F * ks))) break;
     if ((rc = A.alloc(&c->qc, BN * c->hh * (cfg->cross_attend_style == 1 ? 2 : 1) * qe))) break;
     if (cfg->cross_attend_style == 1 && (rc = A.alloc(&c->attn2, BN * 2 * c->hh * ks))) break;
-    const size_t nflags = BN / 32 * c->H + 64;
-    if ((rc = A.alloc(&c->attn_part_o, BN * c->H * 8 * 64))) break;
-    if ((rc = A.alloc(&c->attn_part_ml, BN * c->H * 8 * 2))) break;
+    constexpr int kMaxSplits = 12;
+    const size_t nflags = attention_flag_words(c->Bmax, c->H, c->N, kMaxSplits) + 64;
+    const size_t npart = attention_workspace_floats(c->Bmax, c->H, c->N, kMaxSplits);
+    if ((rc = A.alloc(&c->attn_part_o, npart))) break;
+    if ((rc = A.alloc(&c->attn_part_ml, BN * c->H * kMaxSplits * 2))) break;
     if ((rc = A.alloc(&c->attn_flags, nflags))) break;
     if (cudaMemset(c->attn_flags, 0, nflags * sizeof(uint32_t)) != cudaSuccess) {
       set_error("msd_create: cudaMemset failed");
@@ -966,8 +968,8 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
     }
     c->attn_part_o2 = c->attn_part_o; c->attn_part_ml2 = c->attn_part_ml; c->attn_flags2 = c->attn_flags;
     if (cfg->cross_attend_style == 1) {
-      if ((rc = A.alloc(&c->attn_part_o2, BN * c->H * 8 * 64))) break;
-      if ((rc = A.alloc(&c->attn_part_ml2, BN * c->H * 8 * 2))) break;
+      if ((rc = A.alloc(&c->attn_part_o2, npart))) break;
+      if ((rc = A.alloc(&c->attn_part_ml2, BN * c->H * kMaxSplits * 2))) break;
       if ((rc = A.alloc(&c->attn_flags2, nflags))) break;
       if (cudaMemset(c->attn_flags2, 0, nflags * sizeof(uint32_t)) != cudaSuccess) {
         set_error("msd_create: cudaMemset failed");
@@ -1358,11 +1360,11 @@ int msd_op_attention_trace(const float* q, const float* k, const float* v,
     aa.nbatch = nb; aa.heads = heads; aa.Lq = Lq; aa.Lk = Lk; aa.mask_bits = bits;
     aa.mask_stride_words = Lk / 32; aa.trace = reinterpret_cast<long long*>(trace);
     float *po = nullptr, *pml = nullptr;
-    MSD_TRY(tb.get(&po, static_cast<size_t>(nb) * Lq * heads * 8 * 64));
-    MSD_TRY(tb.get(&pml, static_cast<size_t>(nb) * Lq * heads * 8 * 2));
-    aa.part_o = po; aa.part_ml = pml; aa.max_splits = 8;
+    MSD_TRY(tb.get(&po, attention_workspace_floats(nb, heads, Lq, 12)));
+    MSD_TRY(tb.get(&pml, static_cast<size_t>(nb) * Lq * heads * 12 * 2));
+    aa.part_o = po; aa.part_ml = pml; aa.max_splits = 12;
     uint32_t* fl = nullptr;
-    const size_t nfl = static_cast<size_t>(nb) * heads * ((Lq + 127) / 128) * 4;
+    const size_t nfl = attention_flag_words(nb, heads, Lq, 12);
     MSD_TRY(tb.get(&fl, nfl));
     MSD_CUDA_CHECK(cudaMemsetAsync(fl, 0, nfl * sizeof(uint32_t), st));
     aa.flags = fl;

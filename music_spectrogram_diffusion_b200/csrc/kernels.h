@@ -127,10 +127,12 @@ struct AttnArgs {
   const uint32_t* mask_bits; int mask_stride_words;
   const CUtensorMap* tmap_q; const CUtensorMap* tmap_k; const CUtensorMap* tmap_v;
   long long* trace;  // debugging: per-block clock64 stamps of CTA (0,0,0), see attention kernel
-  // split-KV workspace (optional): part_o [rows*heads*max_splits*64] f32, part_ml [..*2] f32;
-  // splits 0 = choose automatically (attention_pick_splits), capped by max_splits.
+  // split-KV workspace (optional): part_o [attention_workspace_floats(..)] f32, part_ml
+  // [rows*heads*max_splits*2] f32; splits 0 = choose automatically (attention_pick_splits),
+  // capped by max_splits.
   float* part_o; float* part_ml; int splits; int max_splits;
-  // tail mode (needs part_o / part_ml and a zeroed flags array of nbatch*heads*(Lq/128)*4 words):
+  // in-kernel merges (tail mode of the 128-key instance, owner merge of the 64-key instance) need
+  // part_o / part_ml and a zeroed flags array of attention_flag_words(..) words:
   // tail 0 = choose automatically (attention_pick_tail), > 0 = forced, < 0 = off.
   uint32_t* flags; int tail;
   // K, V and mask_bits were written well before the preceding kernel (safe to read ahead of the
@@ -140,6 +142,9 @@ struct AttnArgs {
   // (kv_batch_rows 0 = Lk): lets one source of a concatenated [tokens | context] cache be attended.
   int kv_batch_rows, kv_row0;
 };
+// workspace sizing for part_o (floats) and flags (words) of a launch with up to max_splits splits
+size_t attention_workspace_floats(int nbatch, int heads, int Lq, int max_splits);
+size_t attention_flag_words(int nbatch, int heads, int Lq, int max_splits);
 int attention_pick_splits(int nbatch, int heads, int Lq, int Lk);
 int attention_pick_tail(int nbatch, int heads, int Lq, int Lk);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);

@@ -213,6 +213,7 @@ def test_tail_split_inside_the_step_graph(cuda_device, monkeypatch):
   toks, ctx, cmask = H.make_batch(B, Ts, Cs, seed=8, pad_second=True)
   b = H.torch_batch(toks, ctx, cmask, cuda_device)
   outs = []
+  monkeypatch.setenv('MSD_ATTN_BKV', '128')   # the tail split belongs to the 128-key instance
   for tail in ('-1', '0'):
     monkeypatch.setenv('MSD_ATTN_TAIL', tail)
     eng = H.build_engine(t5, Ts, Ns, Cs, B, steps, 2.0, params)
@@ -230,6 +231,38 @@ def test_tail_split_inside_the_step_graph(cuda_device, monkeypatch):
   assert err.mean().item() < 1e-2, (err.mean().item(), err.max().item())
   assert (err > 0.1).float().mean().item() < 1e-2
   assert not torch.equal(plain, split)                                   # the split really ran
+
+
+def test_owner_merge_inside_the_step_graph(cuda_device, monkeypatch):
+  """64-key instance: a cross-attention whose grid is split along the keys (13 x 6 heads = 78 CTAs
+  -> 3 splits = 234 CTAs, one wave of two CTAs per SM) with the owner CTAs merging their partners'
+  partials inside the kernel; the flag words must re-arm across layers, steps and calls.  Compared
+  with the same engine using the combine kernel (same math, different summation order) and with
+  the 128-key instance."""
+  t5 = config.t5_small()
+  Ts, Ns, Cs, B, steps = 2048, 256, 256, 13, 3
+  params = weights.synthetic_params(t5, Ts, Ns, Cs, seed=2)
+  toks, ctx, cmask = H.make_batch(B, Ts, Cs, seed=8, pad_second=True)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  outs = {}
+  for name, env in (('merge', {'MSD_ATTN_BKV': '64', 'MSD_ATTN_MERGE': '1'}),
+                    ('combine', {'MSD_ATTN_BKV': '64', 'MSD_ATTN_MERGE': '0'}),
+                    ('bkv128', {'MSD_ATTN_BKV': '128', 'MSD_ATTN_MERGE': '0'})):
+    for k, v in env.items():
+      monkeypatch.setenv(k, v)
+    eng = H.build_engine(t5, Ts, Ns, Cs, B, steps, 2.0, params)
+    eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+               b['encoder_continuous_mask'])
+    first, second = eng.sample(seed=3).clone(), eng.sample(seed=3).clone()
+    assert torch.equal(first, second), name                 # deterministic, flags re-armed
+    assert torch.isfinite(first).all(), name
+    outs[name] = first
+    eng.close()
+  span = 4.0 - np.log(1e-5)
+  for other in ('combine', 'bkv128'):
+    err = (outs['merge'] - outs[other]).abs() / span * 2.0
+    assert err.mean().item() < 1e-2, (other, err.mean().item(), err.max().item())
+    assert (err > 0.1).float().mean().item() < 1e-2, other
 
 
 def test_jax_random_stream_on_device_matches_numpy(cuda_device):

@@ -33,9 +33,11 @@ def test_dense_general(cuda_device, M, N, K, variant, block_n):
     (1, 2, 256, 2304, 5, True), (2, 2, 256, 768, 2, 'head'), (3, 2, 128, 256, 1, True),
     (8, 12, 256, 768, 0, False), (8, 12, 256, 2304, 0, True)])
 def test_dot_product_attention_tail_split(cuda_device, monkeypatch, nb, heads, Lq, Lk, tail, masked):
-  """Long/short CTA pairs with the in-kernel merge (tail 0 = the automatic choice, which is active
-  for the 96-CTA grids of the last two cases); run twice to check the hand-shake words re-arm."""
+  """128-key instance: long/short CTA pairs with the in-kernel merge (tail 0 = the automatic
+  choice, which is active for the 96-CTA grids of the last two cases); run twice to check the
+  hand-shake words re-arm."""
   from music_spectrogram_diffusion_b200 import engine
+  monkeypatch.setenv('MSD_ATTN_BKV', '128')
   monkeypatch.setenv('MSD_ATTN_SPLITS', '1')
   monkeypatch.setenv('MSD_ATTN_TAIL', str(tail))
   g = torch.Generator().manual_seed(nb * 77 + Lk + tail)
@@ -67,15 +69,24 @@ def test_dot_product_attention_tail_split(cuda_device, monkeypatch, nb, heads, L
     assert err < 3e-2, f'max err {err}'
 
 
+@pytest.mark.parametrize('bkv,merge', [(64, 1), (64, 0), (128, 0)])
 @pytest.mark.parametrize('splits', [0, 1, 3])
 @pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
     (1, 1, 128, 128, False), (2, 2, 128, 256, False), (2, 3, 256, 384, True),
-    (1, 2, 256, 2304, True), (3, 2, 128, 128, True), (2, 2, 256, 768, True)])
-def test_dot_product_attention(cuda_device, monkeypatch, nb, heads, Lq, Lk, masked, splits):
-  """splits: 0 = automatic split-KV choice, 1 = single pass, 3 = forced 3-way split + combine."""
+    (1, 2, 256, 2304, True), (3, 2, 128, 128, True), (2, 2, 256, 768, True),
+    (16, 12, 256, 256, False), (8, 12, 256, 2304, True)])
+def test_dot_product_attention(cuda_device, monkeypatch, nb, heads, Lq, Lk, masked, splits, bkv, merge):
+  """Both instances of the kernel (64-key blocks, two CTAs per SM; 128-key blocks, one CTA per
+  SM).  splits: 0 = automatic split-KV choice, 1 = single pass, 3 = forced 3-way split; merge:
+  partials merged by the owner CTA inside the kernel (1) or by the combine kernel (0).  The last
+  two shapes are the B = 8 decoder's self- and cross-attention.  Run twice: the merge flags re-arm."""
   from music_spectrogram_diffusion_b200 import engine
-  if splits == 3 and (Lk // 128) % 3:
+  if splits == 3 and (Lk // bkv) % 3:
     pytest.skip('key blocks not divisible by 3')
+  if splits == 1 and merge == 0 and bkv == 64:
+    pytest.skip('same launch as merge=1')
+  monkeypatch.setenv('MSD_ATTN_BKV', str(bkv))
+  monkeypatch.setenv('MSD_ATTN_MERGE', str(merge))
   if splits:
     monkeypatch.setenv('MSD_ATTN_SPLITS', str(splits))
   g = torch.Generator().manual_seed(nb * 1000 + Lk)
@@ -97,11 +108,12 @@ def test_dot_product_attention(cuda_device, monkeypatch, nb, heads, Lq, Lk, mask
                                  v.view(nb, Lk, heads, 64), bias).reshape(nb, Lq, w)
   if masked:
     want = O.zero_activations_if_masked(want, m4)
-  got = engine.op_attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device),
-                            None if mask is None else mask.to(cuda_device), heads).cpu()
-  err = (got - want).abs().max().item()
-  assert torch.isfinite(got).all()
-  assert err < 3e-2, f'max err {err}'
+  for _ in range(2):
+    got = engine.op_attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device),
+                              None if mask is None else mask.to(cuda_device), heads).cpu()
+    err = (got - want).abs().max().item()
+    assert torch.isfinite(got).all()
+    assert err < 3e-2, f'max err {err}'
 
 
 @pytest.mark.parametrize('rows,d,film', [(128, 128, False), (256, 768, True), (100, 512, True)])
