@@ -171,6 +171,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    threadIdx.x == 0;
   long long* ktrp = p.trace + 2 * 64 * 8;  // CTA-level stamps: entry, setup done, loop end, stores done
   if (ktr) ktrp[0] = clock64();
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the swizzled tiles assume a 1024-byte aligned base
   uint8_t* sQ = smem;                                   // [2][16 KB]
   uint8_t* sK = sQ + 2 * Q_BYTES;                       // [KV_STAGES][KV tile]
   uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES][KV tile]
@@ -228,7 +229,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   griddep_launch_dependents();
   if (warp >= 8) {
   if (BKV == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // 384 x 80 = 256 x 104 + 128 x 32
   if (warp == 8) {
     // kv_static: K, V and the key mask were written long before the preceding kernel (the
     // cross-attention cache of a diffusion step), so the first ring-full of K/V tiles is
