@@ -347,7 +347,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int nact = 0;
       for (int j = kb0; j < nkb; ++j) nact += block_active(act, j) ? 1 : 0;
       const bool pingpong = (nq == 2);
-      if (pingpong && tile == 1 && nact > 0) named_barrier_arrive(2, 256);  // tile 0 goes first
+      // barrier ids as immediates (2: tile 0 may run its exps, 3: tile 1 may)
+      auto turn_sync = [&]() {
+        if (tile == 0) named_barrier_sync_c<2>(256);
+        else named_barrier_sync_c<3>(256);
+      };
+      auto turn_give = [&]() {   // let the OTHER tile run
+        if (tile == 0) named_barrier_arrive_c<3>(256);
+        else named_barrier_arrive_c<2>(256);
+      };
+      if (pingpong && tile == 1 && nact > 0) named_barrier_arrive_c<2>(256);  // tile 0 goes first
       constexpr float RESCALE_THRESHOLD = 5.545177444f;  // 8 * ln 2: P stays below 2^8
       int it = 0;
       for (int j = kb0; j < nkb; ++j) {
@@ -424,7 +433,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         const float mb = m * LOG2E;
         if (tr) trp[3] = clock64();
-        if (pingpong) named_barrier_sync(2 + tile, 256);  // my turn on the SFU
+        if (pingpong) turn_sync();  // my turn on the SFU
         if (tr) trp[4] = clock64();
         // p = exp(s - m) as bf16 pairs (packed in place into s[c][0..15]), row sum in fp32.
         const uint64_t l2e2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
@@ -433,7 +442,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // overlap the remaining adds / packs and the P store below (the very last hand-over has no
         // taker and is skipped)
         auto handover = [&]() {
-          if (pingpong && !(tile == 1 && it + 1 == nact)) named_barrier_arrive(2 + (tile ^ 1), 256);
+          if (pingpong && !(tile == 1 && it + 1 == nact)) turn_give();
         };
         // Two copies of the phase behind a warp-uniform branch: with every key of the block
         // attendable (the common case) no select instructions are issued.

@@ -161,6 +161,17 @@ __device__ __forceinline__ void tma_store_wait_read() {  // smem of all but N gr
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+// Compile-time barrier ids: with the id in a register ptxas must assume that all 16 hardware
+// barriers are used, which limits the kernel to ONE CTA per SM (the SM's 16 barriers are shared by
+// its resident CTAs).
+template <uint32_t kId>
+__device__ __forceinline__ void named_barrier_arrive_c(uint32_t threads) {
+  asm volatile("bar.arrive %0, %1;" ::"n"(kId), "r"(threads) : "memory");
+}
+template <uint32_t kId>
+__device__ __forceinline__ void named_barrier_sync_c(uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"n"(kId), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void named_barrier_arrive(uint32_t id, uint32_t threads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

@@ -573,7 +573,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // after this barrier everyone may write the NEXT chunk's slot: its previous user is the
           // store issued three chunks ago, so at most the two newest groups may still be reading
           if (epi_leader) tma_store_wait_read<2>();
-          named_barrier_sync(1, 128);
+          named_barrier_sync_c<1>(128);
           if (epi_leader) {
             if (tile_row < p.M) {  // M % 128 == 0: a CTA's rows are all valid or all padding
               if (has_res) {
