@@ -166,6 +166,13 @@ int msd_op_dense_variant(const float* a, const float* w, int32_t M, int32_t N, i
 int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t variant,
                    int32_t block_n, int32_t iters, float* ms_out);
 
+/* Micro-benchmark hook: average milliseconds of `iters` back-to-back launches of the bf16
+ * attention kernel (+ its combine kernel when the split is not merged in-kernel) on scratch
+ * buffers filled with small pseudo-random values; kv_static as in the decoder's cross-attention.
+ * The instance / split is chosen as in production (or forced by MSD_ATTN_BKV / _SPLITS / _MERGE). */
+int msd_bench_attention(int32_t nb, int32_t heads, int32_t Lq, int32_t Lk, int32_t iters,
+                        float* ms_out);
+
 /* dot_product_attention (layers.py:109-181) for head_dim 64 with a key-padding mask:
  * q [nb, Lq, heads*64], k/v [nb, Lk, heads*64] f32 device, key_mask [nb, Lk] int32 or NULL,
  * out [nb, Lq, heads*64] f32 device. */

@@ -124,6 +124,7 @@ SYMBOLS = [
     ('msd_op_dense', ctypes.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     ('msd_op_dense_variant', ctypes.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
     ('msd_bench_gemm', ctypes.c_int, [_I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(ctypes.c_float)]),
+    ('msd_bench_attention', ctypes.c_int, [_I, _I, _I, _I, _I, ctypes.POINTER(ctypes.c_float)]),
     ('msd_op_attention', ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     ('msd_op_attention_trace', ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     ('msd_op_rmsnorm_film', ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P]),

@@ -18,6 +18,7 @@
 //                       rescaled in TMEM with tcgen05.ld/st), exact because the final division
 //                       uses the same reference max for numerator and denominator
 // Key blocks whose 128 mask bits are all zero are skipped by every role.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -869,6 +870,19 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   d.tail = tail; d.nbatch = a.nbatch; d.flags = a.flags; d.kv_static = a.kv_static;
   d.kv_batch_rows = kv_batch_rows; d.kv_row0 = a.kv_row0;
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * (tail > 0 ? 2 : splits));
+  if (getenv("MSD_ATTN_DEBUG")) {
+    int occ64 = -1, occ128 = -1;
+    cudaError_t e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, attention_tcgen05_kernel<64>,
+                                                                   ATTN_THREADS, ACfg<64>::SMEM);
+    cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ128, attention_tcgen05_kernel<128>,
+                                                                   ATTN_THREADS, ACfg<128>::SMEM);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, attention_tcgen05_kernel<64>);
+    fprintf(stderr, "[attn] nb=%d Lq=%d Lk=%d bkv=%d ctas=%d splits=%d merge=%d tail=%d slots64=%d occ64=%d(%d) "
+            "occ128=%d(%d) regs64=%d smem64=%d maxdyn=%d\n", a.nbatch, a.Lq, a.Lk, bkv, ctas, splits,
+            d.merge, tail, slots_bkv64(), occ64, (int)e1, occ128, (int)e2, fa.numRegs, ACfg<64>::SMEM,
+            fa.maxDynamicSharedSizeBytes);
+  }
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
   if (bkv == 64)

@@ -1328,6 +1328,60 @@ int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t va
   return 0;
 }
 
+int msd_bench_attention(int32_t nb, int32_t heads, int32_t Lq, int32_t Lk, int32_t iters,
+                        float* ms_out) {
+  MSD_REQUIRE(ms_out && iters > 0, "msd_bench_attention: bad argument");
+  const int w = heads * 64;
+  TempBufs tb;
+  bf16 *qb, *kb, *vb, *ob;
+  float *tmp, *po, *pml;
+  uint32_t* fl;
+  const size_t nq = static_cast<size_t>(nb) * Lq * w, nk = static_cast<size_t>(nb) * Lk * w;
+  MSD_TRY(tb.get(&qb, nq)); MSD_TRY(tb.get(&kb, nk)); MSD_TRY(tb.get(&vb, nk)); MSD_TRY(tb.get(&ob, nq));
+  MSD_TRY(tb.get(&tmp, nk));
+  MSD_TRY(tb.get(&po, attention_workspace_floats(nb, heads, Lq, 12)));
+  MSD_TRY(tb.get(&pml, static_cast<size_t>(nb) * Lq * heads * 12 * 2));
+  const size_t nfl = attention_flag_words(nb, heads, Lq, 12);
+  MSD_TRY(tb.get(&fl, nfl));
+  cudaStream_t st = nullptr;
+  MSD_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  MSD_CUDA_CHECK(cudaMemsetAsync(fl, 0, nfl * sizeof(uint32_t), st));
+  // N(0,1) * 0.3-ish values through the jax generator (any bounded values would do)
+  MSD_TRY(launch_jax_normal(1u, 2u, static_cast<long long>(nk), tmp, st));
+  MSD_TRY(launch_f32_to_bf16(tmp, kb, static_cast<long long>(nk), st));
+  MSD_TRY(launch_f32_to_bf16(tmp, vb, static_cast<long long>(nk), st));
+  MSD_TRY(launch_f32_to_bf16(tmp, qb, static_cast<long long>(nq), st));
+  AttnArgs aa;
+  memset(&aa, 0, sizeof(aa));
+  aa.Q = qb; aa.ldq = w; aa.K = kb; aa.ldk = w; aa.V = vb; aa.ldv = w; aa.O = ob; aa.ldo = w;
+  aa.nbatch = nb; aa.heads = heads; aa.Lq = Lq; aa.Lk = Lk;
+  aa.part_o = po; aa.part_ml = pml; aa.max_splits = 12; aa.flags = fl; aa.kv_static = 1;
+  {
+    const char* f = getenv("MSD_ATTN_SPLITS");
+    aa.splits = f ? atoi(f) : 0;
+    const char* t = getenv("MSD_ATTN_TAIL");
+    aa.tail = t ? atoi(t) : 0;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = 0;
+  for (int i = 0; i < 3 && rc == 0; ++i) rc = launch_attention(aa, st);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters && rc == 0; ++i) rc = launch_attention(aa, st);
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(st);
+  if (rc != 0) return rc;
+  MSD_CUDA_CHECK(e);
+  return 0;
+}
+
 int msd_op_attention(const float* q, const float* k, const float* v, const int32_t* key_mask,
                      int32_t nb, int32_t heads, int32_t Lq, int32_t Lk, float* out, void* stream) {
   return msd_op_attention_trace(q, k, v, key_mask, nb, heads, Lq, Lk, out, nullptr, stream);
