@@ -812,6 +812,30 @@ size_t attention_flag_words(int nbatch, int heads, int Lq, int max_splits) {
   return static_cast<size_t>(nbatch) * heads * ((Lq + BQ - 1) / BQ) * 4 * (max_splits > 1 ? max_splits - 1 : 1);
 }
 
+// debugging aid (MSD_ATTN_DEBUG): what limits the residency of the 64-key instance
+static void attention_debug_occupancy() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int smem_sm = 0, smem_resv = 0, regs_sm = 0, smem_optin = 0;
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&smem_resv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+  cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  fprintf(stderr, "[attn] device: smem/SM=%d reserved/block=%d optin/block=%d regs/SM=%d\n", smem_sm,
+          smem_resv, smem_optin, regs_sm);
+  for (int kb = 64; kb <= 113; kb += 7) {
+    int occ = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tcgen05_kernel<64>, ATTN_THREADS,
+                                                  static_cast<size_t>(kb) * 1024);
+    fprintf(stderr, "[attn] occupancy<64>(dyn smem %d KB) = %d\n", kb, occ);
+  }
+  for (int thr = 128; thr <= 384; thr += 128) {
+    int occ = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tcgen05_kernel<64>, thr, 64 * 1024);
+    fprintf(stderr, "[attn] occupancy<64>(%d threads, 64 KB) = %d\n", thr, occ);
+  }
+}
+
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   static int configured = attention_configure();
   if (configured != 0) return configured;
@@ -871,6 +895,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   d.kv_batch_rows = kv_batch_rows; d.kv_row0 = a.kv_row0;
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * (tail > 0 ? 2 : splits));
   if (getenv("MSD_ATTN_DEBUG")) {
+    static bool once = (attention_debug_occupancy(), true);
+    (void)once;
     int occ64 = -1, occ128 = -1;
     cudaError_t e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, attention_tcgen05_kernel<64>,
                                                                    ATTN_THREADS, ACfg<64>::SMEM);
