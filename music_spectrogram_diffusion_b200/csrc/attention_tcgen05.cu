@@ -713,18 +713,29 @@ static int device_sm_count() {
   return cached;
 }
 
-// CTAs of the 64-key instance that are resident at the same time (2 per SM by construction; the
-// occupancy query also covers a device that grants less, e.g. under an MPS thread limit).
+// CTAs of the 64-key instance that can be resident at the same time.  The runtime's occupancy
+// calculator answers 1 for every kernel that contains tcgen05.alloc (tools/ubench/occ_probe.cu), so
+// the count is derived from the resources themselves: shared memory (+ the per-block reserve),
+// registers and tensor memory (256 of the SM's 512 columns per CTA) -> 2 per SM on B200.
 static int slots_bkv64() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (dev != cached_dev) {
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tcgen05_kernel<64>, ATTN_THREADS,
-                                                      ACfg<64>::SMEM) != cudaSuccess)
-      occ = 0;
-    cached = occ * device_sm_count();
+    int smem_sm = 0, smem_resv = 0, regs_sm = 0;
+    cudaFuncAttributes fa;
+    int per_sm = 0;
+    if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&smem_resv, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev) == cudaSuccess &&
+        cudaFuncGetAttributes(&fa, attention_tcgen05_kernel<64>) == cudaSuccess) {
+      const int by_smem = smem_sm / (ACfg<64>::SMEM + smem_resv);
+      const int by_regs = regs_sm / (fa.numRegs * ATTN_THREADS);
+      const int by_tmem = 512 / static_cast<int>(ACfg<64>::TMEM_COLS);
+      per_sm = by_smem < by_regs ? by_smem : by_regs;
+      per_sm = per_sm < by_tmem ? per_sm : by_tmem;
+    }
+    cached = per_sm * device_sm_count();
     cached_dev = dev;
   }
   return cached;
