@@ -584,27 +584,47 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m, l);
       } else {
-        // owner: merge the partners' partials (O = sum_i w_i O_i, l likewise, w_i = exp(m_i - max m))
-        float mm = m;
+        // owner: merge the partners' partials (O = sum_i w_i O_i, l likewise, w_i = exp(m_i - max m)).
+        // At most kMaxPartners partners (the launcher guarantees it), so their (m, l) and weights
+        // live in registers; every L2 round trip of the merge is one batch of independent loads.
+        constexpr int kMaxPartners = 3;
         const size_t wslot0 = wbase * (p.tail > 0 ? 1 : (p.splits > 1 ? p.splits - 1 : 1));
-        for (int pi = 0; pi < npartners; ++pi) {
-          const size_t wslot = wslot0 + pi;
-          for (uint32_t spins = 0; ld_acquire_gpu(p.flags + wslot) == 0u; ++spins) {
-            __nanosleep(100);
-            if (spins > (1u << 24)) __trap();  // partner never published: fail loudly, do not hang
+        float pw[kMaxPartners];   // first the partners' m, then their weights w_i / l_total
+        float plv[kMaxPartners];
+#pragma unroll
+        for (int pi = 0; pi < kMaxPartners; ++pi) {
+          pw[pi] = -INFINITY;
+          plv[pi] = 0.f;
+          if (pi < npartners) {
+            for (uint32_t spins = 0; ld_acquire_gpu(p.flags + wslot0 + pi) == 0u; ++spins) {
+              __nanosleep(64);
+              if (spins > (1u << 24)) __trap();  // partner never published: fail loudly, do not hang
+            }
           }
-          const float2 ml =
-              __ldcg(reinterpret_cast<const float2*>(p.part_o + wslot * SLOT_FLOATS + 32 * HD) + lane);
-          mm = fmaxf(mm, ml.x);
         }
-        const float wl = (m == -INFINITY) ? 0.f : ex2_approx((m - mm) * LOG2E);
+#pragma unroll
+        for (int pi = 0; pi < kMaxPartners; ++pi) {
+          if (pi < npartners) {
+            const float2 ml = __ldcg(
+                reinterpret_cast<const float2*>(p.part_o + (wslot0 + pi) * SLOT_FLOATS + 32 * HD) + lane);
+            pw[pi] = ml.x;
+            plv[pi] = ml.y;
+          }
+        }
+        float mm = m;
+#pragma unroll
+        for (int pi = 0; pi < kMaxPartners; ++pi) mm = fmaxf(mm, pw[pi]);
+        float wl = (m == -INFINITY) ? 0.f : ex2_approx((m - mm) * LOG2E);
         float lt = l * wl;
-        for (int pi = 0; pi < npartners; ++pi) {
-          const float2 ml = __ldcg(
-              reinterpret_cast<const float2*>(p.part_o + (wslot0 + pi) * SLOT_FLOATS + 32 * HD) + lane);
-          lt += (ml.x == -INFINITY) ? 0.f : ml.y * ex2_approx((ml.x - mm) * LOG2E);
+#pragma unroll
+        for (int pi = 0; pi < kMaxPartners; ++pi) {
+          pw[pi] = (pw[pi] == -INFINITY) ? 0.f : ex2_approx((pw[pi] - mm) * LOG2E);
+          lt = fmaf(plv[pi], pw[pi], lt);
         }
         const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+        wl *= inv;
+#pragma unroll
+        for (int pi = 0; pi < kMaxPartners; ++pi) pw[pi] *= inv;
         // Coalesced store: each warp transposes its 32 rows x 128 B through its own 4 KB slice of
         // the (now idle) P tile, then writes whole 128-byte row segments (8 lanes per row); the
         // thread-per-row store cost ~3000 cycles per CTA (32 cache lines per instruction).
@@ -614,21 +634,32 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int c = 0; c < 2; ++c) {
           float o[32];
           load_half(c, o);
-          const float wli = wl * inv;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= wli;
-          for (int pi = 0; pi < npartners; ++pi) {
-            const float* slot = p.part_o + (wslot0 + pi) * SLOT_FLOATS;
-            const float2 ml = __ldcg(reinterpret_cast<const float2*>(slot + 32 * HD) + lane);
-            const float ws = (ml.x == -INFINITY) ? 0.f : ex2_approx((ml.x - mm) * LOG2E) * inv;
-            const float4* po = reinterpret_cast<const float4*>(slot);
+          for (int i = 0; i < 32; ++i) o[i] *= wl;
+          if (npartners > 0) {
+            // 16 columns at a time: 4 float4 of every partner in flight together
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 v = __ldcg(po + (c * 8 + q) * 32 + lane);
-              o[4 * q + 0] = fmaf(v.x, ws, o[4 * q + 0]);
-              o[4 * q + 1] = fmaf(v.y, ws, o[4 * q + 1]);
-              o[4 * q + 2] = fmaf(v.z, ws, o[4 * q + 2]);
-              o[4 * q + 3] = fmaf(v.w, ws, o[4 * q + 3]);
+            for (int h = 0; h < 2; ++h) {
+              float4 v[kMaxPartners][4];
+#pragma unroll
+              for (int pi = 0; pi < kMaxPartners; ++pi)
+                if (pi < npartners) {
+                  const float4* po = reinterpret_cast<const float4*>(p.part_o + (wslot0 + pi) * SLOT_FLOATS);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) v[pi][q] = __ldcg(po + (c * 8 + h * 4 + q) * 32 + lane);
+                }
+#pragma unroll
+              for (int pi = 0; pi < kMaxPartners; ++pi)
+                if (pi < npartners) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const int i0 = (h * 4 + q) * 4;
+                    o[i0 + 0] = fmaf(v[pi][q].x, pw[pi], o[i0 + 0]);
+                    o[i0 + 1] = fmaf(v[pi][q].y, pw[pi], o[i0 + 1]);
+                    o[i0 + 2] = fmaf(v[pi][q].z, pw[pi], o[i0 + 2]);
+                    o[i0 + 3] = fmaf(v[pi][q].w, pw[pi], o[i0 + 3]);
+                  }
+                }
             }
           }
 #pragma unroll
@@ -744,21 +775,26 @@ static int slots_bkv64() {
 // Which instance runs: 64-key blocks (2 CTAs per SM) unless MSD_ATTN_BKV=128 asks for the
 // one-CTA-per-SM kernel (kept for comparison and as the fallback when the device grants only one
 // CTA of the small instance per SM).
-static int attention_bkv(int Lk) {
+static int attention_bkv(int Lk, int ctas) {
   const char* e = getenv("MSD_ATTN_BKV");  // read per launch: the tests switch instances
   const int forced = e ? atoi(e) : 0;
   if (forced == 128 || forced == 64) return (forced == 64 && Lk % 64 == 0) ? 64 : 128;
-  return (Lk % 64 == 0 && slots_bkv64() >= 2 * device_sm_count()) ? 64 : 128;
+  // measured on B200 (tools/attn_bench.py): the two-CTAs-per-SM instance wins once the grid covers
+  // more than half of the SMs (B = 8: self-attention 13.9 vs 17.3 us, token encoder 193 vs 210 us);
+  // small grids (one segment: 12-24 CTAs) are latency chains where the 128-key blocks' fewer
+  // per-block hand-offs win (cross 16.5 vs 24.2 us)
+  return (Lk % 64 == 0 && slots_bkv64() >= 2 * device_sm_count() && 2 * ctas > device_sm_count())
+             ? 64 : 128;
 }
 
 int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
-  if (attention_bkv(Lk) == 64) {
+  if (attention_bkv(Lk, ctas) == 64) {
     // every CTA of the launch should be resident at once (one wave of 2 CTAs per SM): the largest
     // split count that fits, with at least four 64-key blocks per CTA
     const int nkb = Lk / 64, slots = slots_bkv64();
     int best = 1;
-    for (int s = 2; s <= 12; ++s)
+    for (int s = 2; s <= 4; ++s)   // <= 3 partners: the owner CTA merges them in-kernel
       if (nkb % s == 0 && nkb / s >= 4 && ctas * s <= slots) best = s;
     return best;
   }
@@ -780,8 +816,8 @@ int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
 // (several rounds).  Cost model in key-block units with a fixed per-CTA cost F (setup + epilogue,
 // measured ~4.5 on B200: 18 blocks / 96 CTAs -> tail 4).
 int attention_pick_tail(int nbatch, int heads, int Lq, int Lk) {
-  if (attention_bkv(Lk) == 64) return 0;
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
+  if (attention_bkv(Lk, ctas) == 64) return 0;
   const int nkb = Lk / 128;
   const int sms = device_sm_count();
   if (ctas < sms / 2 || ctas >= sms || nkb < 6) return 0;
@@ -850,7 +886,7 @@ static void attention_debug_occupancy() {
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   static int configured = attention_configure();
   if (configured != 0) return configured;
-  const int bkv = attention_bkv(a.Lk);
+  const int bkv = attention_bkv(a.Lk, ((a.Lq + 2 * BQ - 1) / (2 * BQ)) * a.heads * a.nbatch);
   MSD_REQUIRE(a.Lq % BQ == 0 && a.Lk % 128 == 0,
               "attention: Lq=%d and Lk=%d must be multiples of 128", a.Lq, a.Lk);
   MSD_REQUIRE(a.Lk / bkv <= 64, "attention: Lk=%d exceeds 64 key blocks", a.Lk);
@@ -889,8 +925,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   // the whole grid must be resident at once.  MSD_ATTN_MERGE=0 forces the combine kernel.
   const char* merge_env = getenv("MSD_ATTN_MERGE");
   const bool merge_allowed = !(merge_env && merge_env[0] == '0');
-  d.merge = (bkv == 64 && splits > 1 && a.flags != nullptr && merge_allowed &&
-             ctas * splits <= slots_bkv64()) ? 1 : 0;
+  d.merge = (bkv == 64 && splits > 1 && splits <= 4 && a.flags != nullptr && merge_allowed &&
+             ctas * splits <= slots_bkv64()) ? 1 : 0;   // the owner keeps <= 3 partners in registers
   int tail = 0;
   if (bkv == 128 && splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr &&
       a.tail >= 0)
