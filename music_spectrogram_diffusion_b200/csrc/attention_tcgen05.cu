@@ -172,6 +172,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    threadIdx.x == 0;
   long long* ktrp = p.trace + 2 * 64 * 8;  // CTA-level stamps: entry, setup done, loop end, stores done
   if (ktr) ktrp[0] = clock64();
+  // debugging: per-CTA (smid, start, end) in nanoseconds of the global timer, after the per-block
+  // stamps and the 8 CTA-level stamps of the trace buffer
+  long long* ctr = nullptr;
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    const int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (lin < 1024) {
+      ctr = p.trace + 2 * 64 * 8 + 8 + lin * 3;
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      ctr[0] = smid;
+      ctr[1] = t;
+    }
+  }
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the swizzled tiles assume a 1024-byte aligned base
   uint8_t* sQ = smem;                                   // [2][16 KB]
   uint8_t* sK = sQ + 2 * Q_BYTES;                       // [KV_STAGES][KV tile]
@@ -690,6 +705,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   __syncthreads();
   if (ktr) ktrp[4] = clock64();
+  if (ctr != nullptr) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ctr[2] = t;
+  }
   if (warp == 9) {
     tc_fence_after_sync();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

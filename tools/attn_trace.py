@@ -12,14 +12,39 @@ k = torch.randn(nb, Lk, w, device=dev) * 0.3
 v = torch.randn(nb, Lk, w, device=dev)
 mask = torch.ones(nb, Lk, dtype=torch.int32, device=dev) if os.environ.get('MASK', '1') == '1' else None
 out = torch.empty_like(q)
-trace = torch.zeros(2 * 64 * 8 + 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(2 * 64 * 8 + 8 + 3 * 1024, dtype=torch.int64, device=dev)
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 for _ in range(2):
   rc = lib.msd_op_attention_trace(P(q), P(k), P(v), P(mask) if mask is not None else None, nb, H, Lq, Lk, P(out), P(trace), None)
   assert rc == 0, lib.msd_last_error()
 torch.cuda.synchronize()
 tt = trace.cpu()
-k = tt[2 * 64 * 8:]
+k = tt[2 * 64 * 8:2 * 64 * 8 + 8]
+cta = tt[2 * 64 * 8 + 8:].reshape(1024, 3)
+cta = cta[cta[:, 1] > 0]
+if len(cta):
+  import collections
+  t0g = int(cta[:, 1].min())
+  per_sm = collections.Counter(int(x) for x in cta[:, 0])
+  starts = sorted(int(x) - t0g for x in cta[:, 1]); ends = sorted(int(x) - t0g for x in cta[:, 2])
+  durs = sorted(int(e) - int(s_) for s_, e in zip(cta[:, 1], cta[:, 2]))
+  q = lambda v, f: v[min(len(v) - 1, int(f * len(v)))]
+  print(f'{len(cta)} CTAs on {len(per_sm)} SMs, CTAs per SM: {sorted(collections.Counter(per_sm.values()).items())}')
+  print(f'start ns: min {starts[0]} p25 {q(starts, .25)} p50 {q(starts, .5)} p75 {q(starts, .75)} max {starts[-1]}')
+  print(f'end   ns: min {ends[0]} p25 {q(ends, .25)} p50 {q(ends, .5)} p75 {q(ends, .75)} max {ends[-1]}')
+  print(f'duration ns: min {durs[0]} p50 {q(durs, .5)} max {durs[-1]}')
+  # overlapping residency: for each SM, the maximum number of CTAs alive at once
+  by_sm = collections.defaultdict(list)
+  for smid, a, b in cta.tolist():
+    by_sm[smid].append((a, b))
+  conc = collections.Counter()
+  for smid, iv in by_sm.items():
+    ev = sorted([(a, 1) for a, b in iv] + [(b, -1) for a, b in iv])
+    cur = mx = 0
+    for _, d in ev:
+      cur += d; mx = max(mx, cur)
+    conc[mx] += 1
+  print(f'max concurrent CTAs per SM: {sorted(conc.items())}')
 t = tt[:2 * 64 * 8].reshape(2, 64, 8)
 nblk = Lk // 128
 print('CTA stamps (cycles from entry): setup_done=%d first_block_start=%d loop_end=%d stores_done=%d after_sync=%d' % (int(k[1]-k[0]), int(t[0,0,0]-k[0]), int(k[2]-k[0]), int(k[3]-k[0]), int(k[4]-k[0])))
