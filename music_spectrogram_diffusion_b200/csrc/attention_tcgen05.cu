@@ -427,7 +427,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       else if (nxt == 2) named_barrier_arrive_c<4>(256);
       else named_barrier_arrive_c<5>(256);
     };
-    if (ring && pos == RING - 1 && rounds > 0) named_barrier_arrive_c<2>(256);  // position 0 goes first
+    // One token in the two-tile ring; TWO in the four-tile ring (they start at positions 0 and 2 and
+    // stay two apart): a single warp per sub-partition cannot keep the SFU busy on its own (the exp
+    // phase of one tile runs at ~14 cycles per MUFU, latency-bound; the pipe takes one per 8), two
+    // tiles in their exp phase at once can.
+    constexpr bool TWO_TOKENS = (NITEMS == 2);
+    if (ring && rounds > 0) {
+      if (pos == RING - 1) named_barrier_arrive_c<2>(256);              // position 0 goes first
+      if (TWO_TOKENS && pos == 1) named_barrier_arrive_c<4>(256);       // and position 2 with it
+    }
     if (tile < nq || NITEMS == 2) {
       const int lg = warp & 3;
       const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
@@ -441,8 +449,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int it = 0;
       int j = kb0 - 1;
       for (int round = 0; round < rounds; ++round) {
-        // the very last hand-over of the ring has no taker and is skipped
-        const bool give = ring && !(pos == RING - 1 && round + 1 == rounds);
+        // the very last hand-over of each token has no taker and is skipped
+        const bool give = ring && !(round + 1 == rounds && (pos == RING - 1 || (TWO_TOKENS && pos == 1)));
         if (round >= nact) {   // nothing left for this tile: keep the token moving
           if (ring) turn_sync();
           if (give) turn_give();
