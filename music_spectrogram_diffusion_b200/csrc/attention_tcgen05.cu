@@ -33,40 +33,29 @@ namespace {
 constexpr int BQ = 128;   // queries per tile
 constexpr int HD = 64;    // head dim
 constexpr int Q_BYTES = BQ * HD * 2;         // 16 KB per tile
+constexpr int ATTN_THREADS = 384;  // warps 0-3 / 4-7 softmax tile 0 / 1, 8 TMA, 9 MMA, 10-11 idle
 constexpr float LOG2E = 1.4426950408889634f;
 
-// Two instances:
-//   <128, 1>: 128-key blocks, one (query-pair, head, batch) item per CTA, one CTA per SM (193 KB of
-//             shared memory, 384 TMEM columns): two query tiles in flight per SM.  The per-tile
-//             chain of a key block (S wait, TMEM load, max, exp, P store: ~3150 cycles, clock64
-//             trace in profiles/) runs strictly in sequence, so with two tiles the SFU is busy
-//             ~65 % and the issue slots ~26 %: latency-bound.  Best for small grids (one segment).
-//   <64, 2>:  64-key blocks and TWO items per CTA (each with its own TMA warp, MMA warp, K/V ring,
-//             P tiles and 256 TMEM columns): four query tiles in flight per SM, whose SFU-bound exp
-//             phases take turns in a token ring over named barriers.  (Two independent CTAs per SM
-//             do not interleave: the warp scheduler serves the higher warp slots first, so one
-//             CTA ran at full speed and the other starved -- measured, profiles/.)
-template <int BKV, int NITEMS>
+// Two instances, by keys per block:
+//   BKV 128: one CTA per SM (193 KB of shared memory, 384 TMEM columns); two query tiles in flight
+//            per SM.  The per-tile chain of a key block (S wait, TMEM load, max, exp, P store: ~3150
+//            cycles, clock64 trace in profiles/) runs strictly in sequence, so with two tiles the SFU
+//            is busy ~65 % and the issue slots ~26 %: latency-bound.
+//   BKV 64:  half-size K/V stages and P tiles, 256 TMEM columns, 104 registers per softmax thread:
+//            TWO CTAs per SM, i.e. four query tiles in flight per SM, whose phases interleave on
+//            the sub-partitions; grids of up to 2 x SMs CTAs run as a single wave (B = 8
+//            self-attention: 192 CTAs).
+template <int BKV>
 struct ACfg {
   static constexpr int KV_TILE_BYTES = BKV * HD * 2;   // 16 / 8 KB
   static constexpr int KV_STAGES = 3;
   static constexpr int P_BYTES = BQ * BKV * 2;         // 32 / 16 KB per tile ([128 x 64] sub-tiles)
   static constexpr int NCH = BKV / 32;                 // 32-column chunks of a logits row
   static constexpr int WPB = BKV / 32;                 // mask words per key block
-  static constexpr int ITEM_TMEM = 2 * BKV + 128;      // S0 S1 (BKV each) PV0 PV1 (64 each)
-  static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr int ITEM_SMEM = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES;
-  static constexpr int ITEM_BARS = 16;                 // uint64 slots per item (13 used)
-  static constexpr int SMEM = NITEMS * ITEM_SMEM + NITEMS * ITEM_BARS * 8 + 64;
-  // warps: 8 softmax warps per item, then one TMA warp per item, then one MMA warp per item,
-  // padded to a whole warpgroup (setmaxnreg is a warpgroup-wide instruction)
-  static constexpr int SOFTMAX_WARPS = 8 * NITEMS;
-  static constexpr int THREADS = (SOFTMAX_WARPS + 4) * 32;   // 384 / 640
-  // register pool: THREADS x launch registers = softmax threads x SOFTMAX_REGS + 128 x OTHER_REGS
-  static constexpr int SOFTMAX_REGS = NITEMS == 1 ? 224 : 104;
-  static constexpr int OTHER_REGS = 56;
+  static constexpr uint32_t TMEM_COLS = BKV == 128 ? 512 : 256;  // S0 S1 (BKV each) PV0 PV1 (64 each)
+  static constexpr int SMEM = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES + 256;
+  static constexpr int MIN_CTAS = BKV == 128 ? 1 : 2;
 };
-static_assert(ACfg<64, 2>::ITEM_TMEM * 2 <= 512 && ACfg<128, 1>::ITEM_TMEM <= 512, "TMEM budget");
 
 struct AttnDev {
   bf16* O;
@@ -168,18 +157,16 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // stores / loads) followed by [32 lanes] float2 (m, l).
 constexpr int SLOT_FLOATS = 32 * HD + 64;
 
-template <int BKV, int NITEMS>
-__global__ void __launch_bounds__(ACfg<BKV, NITEMS>::THREADS, 1)
+template <int BKV>
+__global__ void __launch_bounds__(ATTN_THREADS, ACfg<BKV>::MIN_CTAS)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const AttnDev p) {
-  using Cfg = ACfg<BKV, NITEMS>;
+  using Cfg = ACfg<BKV>;
   constexpr int KV_STAGES = Cfg::KV_STAGES;
   constexpr int KV_TILE_BYTES = Cfg::KV_TILE_BYTES;
   constexpr int P_BYTES = Cfg::P_BYTES;
   constexpr int NCH = Cfg::NCH;
-  constexpr int SW = Cfg::SOFTMAX_WARPS;       // first non-softmax warp
-  constexpr int RING = 2 * NITEMS;             // tiles taking turns on the SFU
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const bool ktr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
                    threadIdx.x == 0;
@@ -201,52 +188,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   }
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the swizzled tiles assume a 1024-byte aligned base
-
-  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
-  const int lane = threadIdx.x & 31;
-  // which item of this CTA the warp works for: softmax warps 8i .. 8i+7, TMA warp SW + i, MMA
-  // warp SW + NITEMS + i (the remaining warps of the last warpgroup idle)
-  const int il = warp < SW ? (warp >> 3) : ((warp - SW) < NITEMS ? warp - SW : (warp - SW - NITEMS) % NITEMS);
-  const bool is_tma = warp >= SW && warp < SW + NITEMS;
-  const bool is_mma = warp >= SW + NITEMS && warp < SW + 2 * NITEMS;
-
-  // ---- item coordinates
-  int qgrp, head, zz;
-  bool item_valid = true;
-  const int qgroups = (p.Lq + 2 * BQ - 1) / (2 * BQ);
-  if (NITEMS == 1) {
-    qgrp = blockIdx.x; head = blockIdx.y; zz = blockIdx.z;
-  } else {
-    // 1-D grid over pairs of items; item index = (zz * heads + head) * qgroups + qgrp
-    const int nz = p.tail > 0 ? 2 * p.nbatch : p.nbatch * p.splits;
-    const int idx = static_cast<int>(blockIdx.x) * NITEMS + il;
-    item_valid = idx < qgroups * p.heads * nz;
-    const int safe = item_valid ? idx : 0;
-    qgrp = safe % qgroups;
-    head = (safe / qgroups) % p.heads;
-    zz = safe / (qgroups * p.heads);
-  }
-  const int role = p.tail > 0 ? zz / p.nbatch : 0;
-  const int b = p.tail > 0 ? zz - role * p.nbatch : zz / p.splits;
-  const int split = p.tail > 0 ? 0 : zz - b * p.splits;
-  const int q0 = qgrp * 2 * BQ;                       // first query row of this item
-  const int nq = (p.Lq - q0 >= 2 * BQ) ? 2 : 1;       // query tiles of this item
-  const int nkb_all = p.Lk / BKV;
-  // this item's key blocks [kb0, nkb)
-  const int kb0 = p.tail > 0 ? (role ? nkb_all - p.tail : 0) : split * nkb_all / p.splits;
-  const int nkb = !item_valid ? kb0
-                              : (p.tail > 0 ? (role ? nkb_all : nkb_all - p.tail)
-                                            : (split + 1) * nkb_all / p.splits);
-  const uint32_t* mrow =
-      p.mask_bits ? p.mask_bits + static_cast<size_t>(b) * p.mask_stride_words : nullptr;
-
-  // ---- per-item shared memory, barriers and tensor memory
-  uint8_t* sQ = smem + il * Cfg::ITEM_SMEM;             // [2][16 KB]
+  uint8_t* sQ = smem;                                   // [2][16 KB]
   uint8_t* sK = sQ + 2 * Q_BYTES;                       // [KV_STAGES][KV tile]
   uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES][KV tile]
   uint8_t* sP = sV + KV_STAGES * KV_TILE_BYTES;         // [2][P tile]
-  uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem + NITEMS * Cfg::ITEM_SMEM);
-  uint64_t* bars = bars_all + il * Cfg::ITEM_BARS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
   uint64_t* q_full = bars;                  // 1
   uint64_t* kv_full = bars + 1;             // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES; // [KV_STAGES]
@@ -254,14 +200,28 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint64_t* p_full = s_full + 2;            // [2] (128 arrivals each)
   uint64_t* pv_full = p_full + 2;           // [2]
   uint64_t* s_free = pv_full + 2;           // [2] (128 arrivals: logits copied to registers)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_all + NITEMS * Cfg::ITEM_BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
-  if (is_tma && lane == 0) {
-    if (il == 0) {
-      tma_prefetch_desc(&tmap_q);
-      tma_prefetch_desc(&tmap_k);
-      tma_prefetch_desc(&tmap_v);
-    }
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int qgrp = blockIdx.x, head = blockIdx.y;
+  const int role = p.tail > 0 ? static_cast<int>(blockIdx.z) / p.nbatch : 0;
+  const int b = p.tail > 0 ? static_cast<int>(blockIdx.z) - role * p.nbatch
+                           : static_cast<int>(blockIdx.z) / p.splits;
+  const int split = p.tail > 0 ? 0 : static_cast<int>(blockIdx.z) - b * p.splits;
+  const int q0 = qgrp * 2 * BQ;                       // first query row of this CTA
+  const int nq = (p.Lq - q0 >= 2 * BQ) ? 2 : 1;       // query tiles handled here
+  const int nkb_all = p.Lk / BKV;
+  // this CTA's key blocks [kb0, nkb)
+  const int kb0 = p.tail > 0 ? (role ? nkb_all - p.tail : 0) : split * nkb_all / p.splits;
+  const int nkb = p.tail > 0 ? (role ? nkb_all : nkb_all - p.tail) : (split + 1) * nkb_all / p.splits;
+  const uint32_t* mrow =
+      p.mask_bits ? p.mask_bits + static_cast<size_t>(b) * p.mask_stride_words : nullptr;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -275,23 +235,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     fence_barrier_init();
   }
-  if (warp == SW + NITEMS) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot + il * Cfg::ITEM_TMEM;
+  const uint32_t tmem_base = *tmem_slot;
   if (ktr) ktrp[1] = clock64();
 
   griddep_launch_dependents();
-  if (warp >= SW) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::OTHER_REGS));
-  if (is_tma) {
+  if (warp >= 8) {
+  if (BKV == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // 384 x 80 = 256 x 104 + 128 x 32
+  if (warp == 8) {
     // kv_static: K, V and the key mask were written long before the preceding kernel (the
     // cross-attention cache of a diffusion step), so the first ring-full of K/V tiles is
     // requested ahead of the dependency wait; only Q comes from the preceding kernel.
     if (!p.kv_static) griddep_wait();
     const uint64_t act = active_blocks<Cfg::WPB>(mrow, nkb_all, lane);
-    if (lane == 0 && item_valid) {
+    if (lane == 0) {
       int it = 0, j = kb0;
       auto load_kv = [&](int jb) {
         const int s = it % KV_STAGES;
@@ -314,10 +275,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (; j < nkb; ++j)
         if (block_active(act, j)) load_kv(j);
     }
-  } else if (is_mma) {
+  } else if (warp == 9) {
     if (!p.kv_static) griddep_wait();  // mask words may come from the previous kernel
     const uint64_t act = active_blocks<Cfg::WPB>(mrow, nkb_all, lane);
-    if (lane == 0 && item_valid) {
+    if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P K-major, V MN-major
       // descriptor low words (address >> 4 | LBO); stepping = adding (bytes >> 4)
@@ -381,62 +342,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   } else {
     // ------------------------- softmax / output warp groups -------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::SOFTMAX_REGS));
-    const int tile = (warp >> 2) & 1;  // warps 8i..8i+3: tile 0 of item i, 8i+4..8i+7: tile 1
+    if (BKV == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int tile = warp >> 2;  // 0: warps 0..3, 1: warps 4..7
     if (!p.kv_static) griddep_wait();  // mask words may come from the previous kernel
     const uint64_t act = active_blocks<Cfg::WPB>(mrow, nkb_all, lane);
     griddep_wait();  // O is written by these warps
-    int nact = 0;
-    for (int j = kb0; j < nkb; ++j) nact += block_active(act, j) ? 1 : 0;
-    // ---- turn-taking on the SFU-bound exp phase: a token travels round the RING tiles of the CTA
-    // (named barrier 2 + position: "this tile may run its exps"); without it the warpgroups run in
-    // lockstep and collide on the SFU while it idles during their max / store / wait phases, and
-    // the scheduler's fixed priority (higher warp slots first) starves the low ones.  Ring order:
-    // (item 0, tile 0), (item 1, tile 0), (item 0, tile 1), (item 1, tile 1); every tile takes
-    // `rounds` turns (the largest block count of the CTA's items), idle ones just pass the token.
-    int rounds = nact;
-    bool ring = (nq == 2);
-    if (NITEMS == 2) {
-      // the other item's block count: its coordinates follow from the item index
-      const int nz = p.tail > 0 ? 2 * p.nbatch : p.nbatch * p.splits;
-      const int oidx = static_cast<int>(blockIdx.x) * NITEMS + (il ^ 1);
-      int onact = 0;
-      if (oidx < qgroups * p.heads * nz) {
-        const int ozz = oidx / (qgroups * p.heads);
-        const int ob = ozz / p.splits, osplit = ozz - ob * p.splits;
-        const uint32_t* omrow =
-            p.mask_bits ? p.mask_bits + static_cast<size_t>(ob) * p.mask_stride_words : nullptr;
-        const uint64_t oact = active_blocks<Cfg::WPB>(omrow, nkb_all, lane);
-        for (int j = osplit * nkb_all / p.splits; j < (osplit + 1) * nkb_all / p.splits; ++j)
-          onact += block_active(oact, j) ? 1 : 0;
-      }
-      rounds = nact > onact ? nact : onact;
-      ring = true;   // the launcher only uses this instance when every item has two query tiles
-    }
-    const int pos = NITEMS == 1 ? tile : tile * NITEMS + il;
-    auto turn_sync = [&]() {
-      if (pos == 0) named_barrier_sync_c<2>(256);
-      else if (pos == 1) named_barrier_sync_c<3>(256);
-      else if (pos == 2) named_barrier_sync_c<4>(256);
-      else named_barrier_sync_c<5>(256);
-    };
-    auto turn_give = [&]() {   // pass the token to the next tile of the ring
-      const int nxt = (pos + 1) % RING;
-      if (nxt == 0) named_barrier_arrive_c<2>(256);
-      else if (nxt == 1) named_barrier_arrive_c<3>(256);
-      else if (nxt == 2) named_barrier_arrive_c<4>(256);
-      else named_barrier_arrive_c<5>(256);
-    };
-    // One token in the two-tile ring; TWO in the four-tile ring (they start at positions 0 and 2 and
-    // stay two apart): a single warp per sub-partition cannot keep the SFU busy on its own (the exp
-    // phase of one tile runs at ~14 cycles per MUFU, latency-bound; the pipe takes one per 8), two
-    // tiles in their exp phase at once can.
-    constexpr bool TWO_TOKENS = (NITEMS == 2);
-    if (ring && rounds > 0) {
-      if (pos == RING - 1) named_barrier_arrive_c<2>(256);              // position 0 goes first
-      if (TWO_TOKENS && pos == 1) named_barrier_arrive_c<4>(256);       // and position 2 with it
-    }
-    if (tile < nq || NITEMS == 2) {
+    if (tile < nq) {
       const int lg = warp & 3;
       const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
       const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
@@ -445,18 +357,26 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       uint8_t* sPt = sP + tile * P_BYTES;
       float m = -INFINITY, l = 0.f;  // reference max (natural units) and running sum
       uint32_t s[NCH][32];
+      // Ping-pong of the SFU-bound exp phase between the two tiles' warpgroups (named barriers
+      // 2 + tile: "tile may run its exps"): without it both groups run in lockstep and collide on
+      // the SFU while it idles during their max / store / wait phases (ncu: XU 41 % busy).
+      int nact = 0;
+      for (int j = kb0; j < nkb; ++j) nact += block_active(act, j) ? 1 : 0;
+      const bool pingpong = (nq == 2);
+      // barrier ids as immediates (2: tile 0 may run its exps, 3: tile 1 may)
+      auto turn_sync = [&]() {
+        if (tile == 0) named_barrier_sync_c<2>(256);
+        else named_barrier_sync_c<3>(256);
+      };
+      auto turn_give = [&]() {   // let the OTHER tile run
+        if (tile == 0) named_barrier_arrive_c<3>(256);
+        else named_barrier_arrive_c<2>(256);
+      };
+      if (pingpong && tile == 1 && nact > 0) named_barrier_arrive_c<2>(256);  // tile 0 goes first
       constexpr float RESCALE_THRESHOLD = 5.545177444f;  // 8 * ln 2: P stays below 2^8
       int it = 0;
-      int j = kb0 - 1;
-      for (int round = 0; round < rounds; ++round) {
-        // the very last hand-over of each token has no taker and is skipped
-        const bool give = ring && !(round + 1 == rounds && (pos == RING - 1 || (TWO_TOKENS && pos == 1)));
-        if (round >= nact) {   // nothing left for this tile: keep the token moving
-          if (ring) turn_sync();
-          if (give) turn_give();
-          continue;
-        }
-        do { ++j; } while (!block_active(act, j));
+      for (int j = kb0; j < nkb; ++j) {
+        if (!block_active(act, j)) continue;
         uint32_t mw[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) mw[c] = 0xffffffffu;
@@ -470,7 +390,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
         }
         const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 &&
-                        blockIdx.z == 0 && il == 0 && lg == 0 && lane == 0 && it < 64;
+                        blockIdx.z == 0 && lg == 0 && lane == 0 && it < 64;
         long long* trp = p.trace + (tile * 64 + it) * 8;
         if (tr) trp[0] = clock64();
         mbar_wait(&s_full[tile], it & 1);
@@ -529,11 +449,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         const float mb = m * LOG2E;
         if (tr) trp[3] = clock64();
-        if (ring) turn_sync();  // my turn on the SFU
+        if (pingpong) turn_sync();  // my turn on the SFU
         if (tr) trp[4] = clock64();
         // p = exp(s - m) as bf16 pairs (packed in place into s[c][0..15]), row sum in fp32.
         const uint64_t l2e2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
         uint64_t acc2 = pack2(0.f, 0.f), acc2b = pack2(0.f, 0.f);
+        // the last MUFU of this block has been issued: hand the SFU to the other tile, its exps
+        // overlap the remaining adds / packs and the P store below (the very last hand-over has no
+        // taker and is skipped)
+        auto handover = [&]() {
+          if (pingpong && !(tile == 1 && it + 1 == nact)) turn_give();
+        };
         // Two copies of the phase behind a warp-uniform branch: with every key of the block
         // attendable (the common case) no select instructions are issued.
         auto exp_phase = [&](auto masked_tag) {
@@ -574,16 +500,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
             exp_chunk(2, e[0]);
             finish_chunk(1, e[1]);
             exp_chunk(3, e[1]);
-            // the last MUFU of this block has been issued: pass the token, the next tile's exps
-            // overlap the remaining adds / packs and the P store below
-            if (give) turn_give();
+            handover();
             finish_chunk(2, e[0]);
             finish_chunk(3, e[1]);
           } else {
+            // 104 registers per thread: one 32-wide staging buffer; the second chunk's exps are
+            // issued while the first chunk is summed and packed
             float e0[32], e1[32];
             exp_chunk(0, e0);
             exp_chunk(1, e1);
-            if (give) turn_give();
+            handover();
             finish_chunk(0, e0);
             finish_chunk(1, e1);
           }
@@ -617,7 +543,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         ++it;
       }
       if (ktr) ktrp[2] = clock64();
-      if (item_valid && tile < nq) {
       if (it > 0) {
         mbar_wait(&pv_full[tile], (it - 1) & 1);
         tc_fence_after_sync();
@@ -774,7 +699,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.ldo + ch * 8) = u;
         }
       }
-      }
       if (ktr) ktrp[3] = clock64();
       tc_fence_before_sync();
     }
@@ -786,9 +710,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     ctr[2] = t;
   }
-  if (warp == SW + NITEMS) {
+  if (warp == 9) {
     tc_fence_after_sync();
-    tmem_dealloc<Cfg::TMEM_COLS>(*tmem_slot);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -840,27 +764,58 @@ static int device_sm_count() {
   return cached;
 }
 
-// Items (query-pair, head, batch, split) the dual-item instance keeps in flight in one wave: one
-// CTA per SM (229 KB of shared memory, all 512 TMEM columns), two items per CTA.
-static int slots_bkv64() { return 2 * device_sm_count(); }
+// CTAs of the 64-key instance that can be resident at the same time.  The runtime's occupancy
+// calculator answers 1 for every kernel that contains tcgen05.alloc (tools/ubench/occ_probe.cu), so
+// the count is derived from the resources themselves: shared memory (+ the per-block reserve),
+// registers and tensor memory (256 of the SM's 512 columns per CTA) -> 2 per SM on B200.
+static int slots_bkv64() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cached_dev) {
+    int smem_sm = 0, smem_resv = 0, regs_sm = 0;
+    cudaFuncAttributes fa;
+    int per_sm = 0;
+    if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&smem_resv, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev) == cudaSuccess &&
+        cudaFuncGetAttributes(&fa, attention_tcgen05_kernel<64>) == cudaSuccess) {
+      const int by_smem = smem_sm / (ACfg<64>::SMEM + smem_resv);
+      const int by_regs = regs_sm / (fa.numRegs * ATTN_THREADS);
+      const int by_tmem = 512 / static_cast<int>(ACfg<64>::TMEM_COLS);
+      per_sm = by_smem < by_regs ? by_smem : by_regs;
+      per_sm = per_sm < by_tmem ? per_sm : by_tmem;
+    }
+    cached = per_sm * device_sm_count();
+    cached_dev = dev;
+  }
+  return cached;
+}
 
-// Which instance runs: the dual-item 64-key kernel once the grid covers more than half of the SMs
-// (measured on B200, tools/attn_bench.py), the single-item 128-key kernel for small grids (one
-// segment: 12-24 items are latency chains where fewer, larger blocks win), for query lengths that
-// are not a multiple of 256 and when MSD_ATTN_BKV=128 asks for it.
-static int attention_bkv(int Lk, int Lq, int items) {
+// Which instance runs: 64-key blocks (2 CTAs per SM) unless MSD_ATTN_BKV=128 asks for the
+// one-CTA-per-SM kernel (kept for comparison and as the fallback when the device grants only one
+// CTA of the small instance per SM).
+static int attention_bkv(int Lk, int ctas) {
   const char* e = getenv("MSD_ATTN_BKV");  // read per launch: the tests switch instances
   const int forced = e ? atoi(e) : 0;
-  const bool ok64 = Lk % 64 == 0 && Lq % (2 * BQ) == 0;
-  if (forced == 128 || forced == 64) return (forced == 64 && ok64) ? 64 : 128;
-  return (ok64 && 2 * items > device_sm_count()) ? 64 : 128;
+  if (forced == 128 || forced == 64) return (forced == 64 && Lk % 64 == 0) ? 64 : 128;
+  // Measured on B200 (tools/attn_bench.py, profiles/README.md): the two-CTAs-per-SM instance wins
+  // when the grid has at least one CTA per SM (B = 8 self-attention, 192 CTAs in ONE wave: 13.9 vs
+  // 17.3 us; token encoder, 768 CTAs: 193 vs 210 us).  Two co-resident CTAs do not interleave
+  // evenly (the warp scheduler serves the higher warp slots first: one CTA of an SM runs at full
+  // speed, the other mostly afterwards), so a grid that fits one CTA per SM is still better off
+  // with the 128-key blocks and their long/short tail split (B = 8 cross-attention, 96 CTAs: 34.6
+  // vs 37.4 us), and small grids (one segment: 12-24 CTAs) are latency chains where fewer, larger
+  // blocks win (16.5 vs 24.2 us).
+  return (Lk % 64 == 0 && slots_bkv64() >= 2 * device_sm_count() && ctas >= device_sm_count()) ? 64
+                                                                                                : 128;
 }
 
 int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
-  if (attention_bkv(Lk, Lq, ctas) == 64) {
-    // every item of the launch should be in flight at once (two per SM): the largest split count
-    // that fits, with at least four 64-key blocks per item
+  if (attention_bkv(Lk, ctas) == 64) {
+    // every CTA of the launch should be resident at once (one wave of 2 CTAs per SM): the largest
+    // split count that fits, with at least four 64-key blocks per CTA
     const int nkb = Lk / 64, slots = slots_bkv64();
     int best = 1;
     for (int s = 2; s <= 4; ++s)   // <= 3 partners: the owner CTA merges them in-kernel
@@ -886,7 +841,7 @@ int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
 // measured ~4.5 on B200: 18 blocks / 96 CTAs -> tail 4).
 int attention_pick_tail(int nbatch, int heads, int Lq, int Lk) {
   const int ctas = ((Lq + 2 * BQ - 1) / (2 * BQ)) * heads * nbatch;
-  if (attention_bkv(Lk, Lq, ctas) == 64) return 0;
+  if (attention_bkv(Lk, ctas) == 64) return 0;
   const int nkb = Lk / 128;
   const int sms = device_sm_count();
   if (ctas < sms / 2 || ctas >= sms || nkb < 6) return 0;
@@ -904,10 +859,12 @@ int attention_pick_tail(int nbatch, int heads, int Lq, int Lk) {
 }
 
 int attention_configure() {
-  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 1>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128, 1>::SMEM));
-  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64, 2>::SMEM));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<128>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128>::SMEM));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<64>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64>::SMEM));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<64>,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   MSD_CUDA_CHECK(cudaFuncSetAttribute(attention_combine_kernel,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   return 0;
@@ -929,7 +886,7 @@ size_t attention_flag_words(int nbatch, int heads, int Lq, int max_splits) {
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   static int configured = attention_configure();
   if (configured != 0) return configured;
-  const int bkv = attention_bkv(a.Lk, a.Lq, ((a.Lq + 2 * BQ - 1) / (2 * BQ)) * a.heads * a.nbatch);
+  const int bkv = attention_bkv(a.Lk, ((a.Lq + 2 * BQ - 1) / (2 * BQ)) * a.heads * a.nbatch);
   MSD_REQUIRE(a.Lq % BQ == 0 && a.Lk % 128 == 0,
               "attention: Lq=%d and Lk=%d must be multiples of 128", a.Lq, a.Lk);
   MSD_REQUIRE(a.Lk / bkv <= 64, "attention: Lk=%d exceeds 64 key blocks", a.Lk);
@@ -969,8 +926,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   const char* merge_env = getenv("MSD_ATTN_MERGE");
   const bool merge_allowed = !(merge_env && merge_env[0] == '0');
   d.merge = (bkv == 64 && splits > 1 && splits <= 4 && a.flags != nullptr && merge_allowed &&
-             ctas * splits <= slots_bkv64()) ? 1 : 0;   // the owner keeps <= 3 partners in registers;
-                                                         // every CTA of the grid is resident at once
+             ctas * splits <= slots_bkv64()) ? 1 : 0;   // the owner keeps <= 3 partners in registers
   int tail = 0;
   if (bkv == 128 && splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr &&
       a.tail >= 0)
@@ -986,18 +942,16 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   d.kv_batch_rows = kv_batch_rows; d.kv_row0 = a.kv_row0;
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.nbatch * (tail > 0 ? 2 : splits));
   if (getenv("MSD_ATTN_DEBUG"))
-    fprintf(stderr, "[attn] nb=%d Lq=%d Lk=%d bkv=%d items=%d splits=%d merge=%d tail=%d\n", a.nbatch, a.Lq,
+    fprintf(stderr, "[attn] nb=%d Lq=%d Lk=%d bkv=%d ctas=%d splits=%d merge=%d tail=%d\n", a.nbatch, a.Lq,
             a.Lk, bkv, ctas, splits, d.merge, tail);
   ProfScope prof(KC_ATTENTION, 4.0 * a.nbatch * a.heads * static_cast<double>(a.Lq) * a.Lk * HD,
                  2.0 * a.nbatch * a.heads * HD * (2.0 * a.Lq + 2.0 * a.Lk), stream);
-  if (bkv == 64) {
-    const int items = ctas * splits;
-    MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel<64, 2>, dim3((items + 1) / 2),
-                                 dim3(ACfg<64, 2>::THREADS), ACfg<64, 2>::SMEM, stream, tq, tk, tv, d));
-  } else {
-    MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel<128, 1>, grid, dim3(ACfg<128, 1>::THREADS),
-                                 ACfg<128, 1>::SMEM, stream, tq, tk, tv, d));
-  }
+  if (bkv == 64)
+    MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel<64>, grid, dim3(ATTN_THREADS), ACfg<64>::SMEM,
+                                 stream, tq, tk, tv, d));
+  else
+    MSD_CUDA_CHECK(launch_kernel(attention_tcgen05_kernel<128>, grid, dim3(ATTN_THREADS),
+                                 ACfg<128>::SMEM, stream, tq, tk, tv, d));
   ++g_launch_count;
   if (splits > 1 && !d.merge) {
     const long long n_rh = static_cast<long long>(a.nbatch) * a.Lq * a.heads;
