@@ -405,12 +405,9 @@ def measure_gemm_traffic(args, timeout_s=240):
                  'launches of one uncaptured diffusion step, measured in this run'}
 
 
-def single_song_sample(t5, diff, lengths, device_index, segments=3):
-  """BASELINE config 5 in miniature on one GPU: one synthetic multi-instrument song, segments
-  chained through song.synthesize_song (batch 1, context = previous prediction), timed like the
-  reference's `model_timing` (first segment excluded, beam/evaluation.py:217-220)."""
-  from music_spectrogram_diffusion_b200 import inference, midi_tokens, song
-  model = inference.InferenceModel.from_config(t5, diff, lengths, 'synthetic:0', 1, device_index)
+def synthetic_song_notes(segments, lengths):
+  """A multi-instrument synthetic arrangement covering `segments` 5.12 s segments."""
+  from music_spectrogram_diffusion_b200 import midi_tokens
   rng = np.random.default_rng(5)
   seconds = segments * lengths['targets'] / FRAME_RATE - 0.25
   rows = []
@@ -421,15 +418,59 @@ def single_song_sample(t5, diff, lengths, device_index, segments=3):
       rows.append((t, min(t + d, seconds), int(rng.integers(36, 84)), int(rng.integers(30, 127)),
                    program, False))
       t += float(rng.uniform(0.08, 0.4))
-  out = song.synthesize_song(model, midi_tokens.make_notes(rows), seed=0)
-  timing = out['model_timing']
+  return midi_tokens.make_notes(rows), len(rows)
+
+
+def single_song_sample(t5, diff, lengths, device_index, segments=12, world=1):
+  """BASELINE config 5: ONE synthetic multi-instrument song of `segments` chained 5.12 s segments
+  (61.44 s for 12; batch 1, context = previous prediction), timed like the reference's
+  `model_timing` (first segment excluded, beam/evaluation.py:217-220).
+  N = 1: song.synthesize_song through InferenceModel.predict (host batches, as the reference).
+  N >= 2: ranks 0 and 1 split the classifier-free guidance (conditional pass on one GPU,
+  unconditional on the other, predicted noise exchanged by NVLink stores inside the sampler
+  kernel: distributed.synthesize_song_cfg_split); the chain is serial, so further ranks cannot
+  help this one song and only join the barriers."""
+  import torch
+  from music_spectrogram_diffusion_b200 import distributed as D, inference, midi_tokens, song
+  notes, n_notes = synthetic_song_notes(segments, lengths)
+  model = inference.InferenceModel.from_config(t5, diff, lengths, 'synthetic:0', 1, device_index)
+  ac = model.audio_codec
+  seconds_per_chunk = lengths['targets'] * (ac.hop_size / ac.sample_rate)
+  if world == 1:
+    out = song.synthesize_song(model, notes, seed=0)
+    timing = out['model_timing']
+    per_chunk = timing['prediction_seconds_per_chunk']
+    toks = out['tokens']
+    api = 'song.synthesize_song(InferenceModel(batch_size=1), notes): tokenise + chained predict'
+    gpus_used = 1
+  else:
+    import torch.distributed as dist
+    tk = midi_tokens.tokenize_song(
+        notes, song.event_vocabulary_of(model), inputs_length=lengths['inputs'],
+        frames_per_segment=lengths['targets'], frame_rate=ac.frame_rate, sample_rate=ac.sample_rate,
+        hop_size=ac.hop_size)
+    toks = tk.tokens
+    segs = [torch.from_numpy(np.ascontiguousarray(t)) for t in toks]
+    model.engine  # build before the handles are swapped
+    timings = []
+    mel = D.synthesize_song_cfg_split(model, segs, lengths['targets_context'], 128, seed=0,
+                                      timings=timings)
+    dist.barrier()
+    if mel is None or dist.get_rank() != 0:
+      del model
+      return None
+    per_chunk = float(np.mean(timings))
+    api = ('distributed.synthesize_song_cfg_split: conditional pass on GPU 0, unconditional on GPU 1, '
+           'eps exchanged by peer stores inside the sampler kernel; device-resident chain')
+    gpus_used = 2
   del model
   return {
-      'segments': int(len(out['tokens'])), 'notes': len(rows),
-      'tokens_per_segment': [int((r > 0).sum()) for r in out['tokens']],
-      'seconds_per_segment': timing['prediction_seconds_per_chunk'],
-      'x_realtime': 1.0 / timing['predictions_seconds_per_audio_second'],
-      'api': 'song.synthesize_song(InferenceModel(batch_size=1), notes): tokenise + chained predict',
+      'segments': int(len(toks)), 'notes': n_notes, 'audio_seconds': len(toks) * seconds_per_chunk,
+      'tokens_per_segment': [int((r > 0).sum()) for r in toks],
+      'seconds_per_segment': per_chunk,
+      'x_realtime': seconds_per_chunk / per_chunk,
+      'gpus_used_by_this_song': gpus_used,
+      'api': api,
   }
 
 
@@ -499,6 +540,12 @@ def run_ours(args):
   value = frames / sec
   sec_e2e, wall_e2e, clocks_e2e, _ = timed(host_step, max(1, args.warmup // 2), args.steps)
   value_e2e = frames / sec_e2e
+
+  # ---- BASELINE config 5: one chained song (every rank takes part in the set-up barriers) ----
+  song_result = None
+  if not args.no_song and lengths['inputs'] >= 2048 and args.precision == 'bf16':
+    song_result = single_song_sample(t5, diff, lengths, local, segments=args.song_segments,
+                                     world=world)
 
   # ---- roofline of the dominant kernel class (tcgen05 GEMM), CUDA events per launch -------
   prof = None
@@ -577,8 +624,8 @@ def run_ours(args):
         'in_graph': timeline,
         'attention_tflops': attn_tf,
     }
-    if world == 1 and not args.no_song and lengths['inputs'] >= 2048:
-      line['single_song'] = single_song_sample(t5, diff, lengths, local)
+    if song_result is not None:
+      line['single_song'] = song_result
     if world == 1 and not args.no_cpu_baseline:
       cores = best_thread_count(t5, diff, lengths)
       t_enc, t_step, per_step = cpu_oracle_sample(t5, diff, lengths, args.cpu_steps, cores)
@@ -617,7 +664,9 @@ def main():
                   help='skip the ncu DRAM-traffic measurement of the dominant kernel')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-song', action='store_true',
-                  help='skip the batch-1 chained-song sample (BASELINE config 5 in miniature)')
+                  help='skip the batch-1 chained-song sample (BASELINE config 5)')
+  ap.add_argument('--song-segments', type=int, default=12,
+                  help='segments of the chained song (12 = 61.44 s, BASELINE config 5)')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

@@ -117,6 +117,20 @@ int msd_encode(msd_ctx* ctx, const int32_t* tokens, const float* ctx_features,
 int msd_sample(msd_ctx* ctx, const float* init_z, const float* noise, uint64_t seed,
                float* mel_out, void* stream);
 
+/* ---- one song on two GPUs: classifier-free guidance split (BASELINE config 5) ----
+ * The two decoder passes of a reverse step (diffusion_utils.py:415, 428-429) are independent until
+ * the guidance combine (430-433).  With a peer attached, a context runs ONE of them (role 1: the
+ * conditional pass incl. cross-attention, role 2: the unconditional one) and its sampler kernel
+ * exchanges the 128 KB of predicted noise with the peer by direct NVLink stores plus a flag word
+ * (no NCCL call, no host involvement inside the loop); both GPUs then apply the identical update,
+ * so both hold the same z and the same final mel.  Protocol: each process calls msd_p2p_export,
+ * the 64-byte handles are swapped by any host channel (torch.distributed in distributed.py), each
+ * calls msd_p2p_attach with the OTHER rank's handle, and then both make the same msd_encode /
+ * msd_sample calls.  The processes must live on one node with peer access between the GPUs. */
+int msd_p2p_export(msd_ctx* ctx, void* handle_out /* 64 bytes */);
+int msd_p2p_attach(msd_ctx* ctx, const void* peer_handle /* 64 bytes */, int32_t role);
+int msd_p2p_detach(msd_ctx* ctx);
+
 /* Test hook == module.decode (network.py:561-573) at diffusion step `step_i`
  * (time = (step_i + 1) / num_steps): z [B, targets_length, n_dims] f32 device ->
  * eps_out [B, ...] f32 device.  conditioned = 0 multiplies encodings and masks by 0

@@ -116,6 +116,9 @@ SYMBOLS = [
     ('msd_load_weights', ctypes.c_int, [_P, ctypes.POINTER(MsdTensor), _I]),
     ('msd_encode', ctypes.c_int, [_P, _P, _P, _P, _I, _P]),
     ('msd_sample', ctypes.c_int, [_P, _P, _P, ctypes.c_uint64, _P, _P]),
+    ('msd_p2p_export', ctypes.c_int, [_P, _P]),
+    ('msd_p2p_attach', ctypes.c_int, [_P, _P, _I]),
+    ('msd_p2p_detach', ctypes.c_int, [_P]),
     ('msd_decode_eps', ctypes.c_int, [_P, _P, _I, _I, _P, _P]),
     ('msd_get_encodings', ctypes.c_int, [_P, _P, _P]),
     ('msd_get_step_table', ctypes.c_int, [_P, _P]),

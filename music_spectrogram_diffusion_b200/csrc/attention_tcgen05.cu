@@ -599,47 +599,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m, l);
       } else {
-        // owner: merge the partners' partials (O = sum_i w_i O_i, l likewise, w_i = exp(m_i - max m)).
-        // At most kMaxPartners partners (the launcher guarantees it), so their (m, l) and weights
-        // live in registers; every L2 round trip of the merge is one batch of independent loads.
-        constexpr int kMaxPartners = 3;
+        // owner: merge the partners' partials (O = sum_i w_i O_i / sum_i w_i l_i, w_i = exp(m_i -
+        // max m)).  Partners are handled in groups of kGroup whose loads of one L2 round trip are
+        // all in flight together; any number of partners (the launcher only requires that the whole
+        // grid is resident, so that waiting for them cannot deadlock).
+        constexpr int kGroup = 3;
         const size_t wslot0 = wbase * (p.tail > 0 ? 1 : (p.splits > 1 ? p.splits - 1 : 1));
-        float pw[kMaxPartners];   // first the partners' m, then their weights w_i / l_total
-        float plv[kMaxPartners];
-#pragma unroll
-        for (int pi = 0; pi < kMaxPartners; ++pi) {
-          pw[pi] = -INFINITY;
-          plv[pi] = 0.f;
-          if (pi < npartners) {
-            for (uint32_t spins = 0; ld_acquire_gpu(p.flags + wslot0 + pi) == 0u; ++spins) {
-              __nanosleep(64);
-              if (spins > (1u << 24)) __trap();  // partner never published: fail loudly, do not hang
-            }
-          }
-        }
-#pragma unroll
-        for (int pi = 0; pi < kMaxPartners; ++pi) {
-          if (pi < npartners) {
-            const float2 ml = __ldcg(
-                reinterpret_cast<const float2*>(p.part_o + (wslot0 + pi) * SLOT_FLOATS + 32 * HD) + lane);
-            pw[pi] = ml.x;
-            plv[pi] = ml.y;
+        auto slot_ml = [&](int pi) {
+          return __ldcg(reinterpret_cast<const float2*>(p.part_o + (wslot0 + pi) * SLOT_FLOATS + 32 * HD) + lane);
+        };
+        for (int pi = 0; pi < npartners; ++pi) {
+          for (uint32_t spins = 0; ld_acquire_gpu(p.flags + wslot0 + pi) == 0u; ++spins) {
+            __nanosleep(64);
+            if (spins > (1u << 24)) __trap();  // partner never published: fail loudly, do not hang
           }
         }
         float mm = m;
+        for (int g = 0; g < npartners; g += kGroup) {
+          float pm[kGroup];
 #pragma unroll
-        for (int pi = 0; pi < kMaxPartners; ++pi) mm = fmaxf(mm, pw[pi]);
-        float wl = (m == -INFINITY) ? 0.f : ex2_approx((m - mm) * LOG2E);
-        float lt = l * wl;
+          for (int u = 0; u < kGroup; ++u) pm[u] = (g + u < npartners) ? slot_ml(g + u).x : -INFINITY;
 #pragma unroll
-        for (int pi = 0; pi < kMaxPartners; ++pi) {
-          pw[pi] = (pw[pi] == -INFINITY) ? 0.f : ex2_approx((pw[pi] - mm) * LOG2E);
-          lt = fmaf(plv[pi], pw[pi], lt);
+          for (int u = 0; u < kGroup; ++u) mm = fmaxf(mm, pm[u]);
         }
-        const float inv = lt > 0.f ? 1.0f / lt : 0.f;
-        wl *= inv;
-#pragma unroll
-        for (int pi = 0; pi < kMaxPartners; ++pi) pw[pi] *= inv;
+        const float wl = (m == -INFINITY) ? 0.f : ex2_approx((m - mm) * LOG2E);
+        float lt = l * wl, inv = 0.f;
         // Coalesced store: each warp transposes its 32 rows x 128 B through its own 4 KB slice of
         // the (now idle) P tile, then writes whole 128-byte row segments (8 lanes per row); the
         // thread-per-row store cost ~3000 cycles per CTA (32 cache lines per instruction).
@@ -651,39 +635,51 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           load_half(c, o);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] *= wl;
-          if (npartners > 0) {
-            // 16 columns at a time: 4 float4 of every partner in flight together
+#pragma unroll 1
+          for (int g = 0; g < npartners; g += kGroup) {
+            float pw[kGroup];
+#pragma unroll
+            for (int u = 0; u < kGroup; ++u) {
+              pw[u] = 0.f;
+              if (g + u < npartners) {
+                const float2 ml = slot_ml(g + u);
+                pw[u] = (ml.x == -INFINITY) ? 0.f : ex2_approx((ml.x - mm) * LOG2E);
+                if (c == 0) lt = fmaf(ml.y, pw[u], lt);
+              }
+            }
+            // 16 columns at a time: 4 float4 of every partner of the group in flight together
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              float4 v[kMaxPartners][4];
+              float4 v[kGroup][4];
 #pragma unroll
-              for (int pi = 0; pi < kMaxPartners; ++pi)
-                if (pi < npartners) {
-                  const float4* po = reinterpret_cast<const float4*>(p.part_o + (wslot0 + pi) * SLOT_FLOATS);
+              for (int u = 0; u < kGroup; ++u)
+                if (g + u < npartners) {
+                  const float4* po = reinterpret_cast<const float4*>(p.part_o + (wslot0 + g + u) * SLOT_FLOATS);
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) v[pi][q] = __ldcg(po + (c * 8 + h * 4 + q) * 32 + lane);
+                  for (int q = 0; q < 4; ++q) v[u][q] = __ldcg(po + (c * 8 + h * 4 + q) * 32 + lane);
                 }
 #pragma unroll
-              for (int pi = 0; pi < kMaxPartners; ++pi)
-                if (pi < npartners) {
+              for (int u = 0; u < kGroup; ++u)
+                if (g + u < npartners) {
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
                     const int i0 = (h * 4 + q) * 4;
-                    o[i0 + 0] = fmaf(v[pi][q].x, pw[pi], o[i0 + 0]);
-                    o[i0 + 1] = fmaf(v[pi][q].y, pw[pi], o[i0 + 1]);
-                    o[i0 + 2] = fmaf(v[pi][q].z, pw[pi], o[i0 + 2]);
-                    o[i0 + 3] = fmaf(v[pi][q].w, pw[pi], o[i0 + 3]);
+                    o[i0 + 0] = fmaf(v[u][q].x, pw[u], o[i0 + 0]);
+                    o[i0 + 1] = fmaf(v[u][q].y, pw[u], o[i0 + 1]);
+                    o[i0 + 2] = fmaf(v[u][q].z, pw[u], o[i0 + 2]);
+                    o[i0 + 3] = fmaf(v[u][q].w, pw[u], o[i0 + 3]);
                   }
                 }
             }
           }
+          if (c == 0) inv = lt > 0.f ? 1.0f / lt : 0.f;   // every partner's l has been added by now
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 u;
-            u.x = pack_bf16(o[8 * q + 0], o[8 * q + 1]);
-            u.y = pack_bf16(o[8 * q + 2], o[8 * q + 3]);
-            u.z = pack_bf16(o[8 * q + 4], o[8 * q + 5]);
-            u.w = pack_bf16(o[8 * q + 6], o[8 * q + 7]);
+            u.x = pack_bf16(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
+            u.y = pack_bf16(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
+            u.z = pack_bf16(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
+            u.w = pack_bf16(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
             *reinterpret_cast<uint4*>(stg + lane * 128 + (((c * 4 + q) ^ (lane & 7)) * 16)) = u;
           }
         }
@@ -818,7 +814,7 @@ int attention_pick_splits(int nbatch, int heads, int Lq, int Lk) {
     // split count that fits, with at least four 64-key blocks per CTA
     const int nkb = Lk / 64, slots = slots_bkv64();
     int best = 1;
-    for (int s = 2; s <= 4; ++s)   // <= 3 partners: the owner CTA merges them in-kernel
+    for (int s = 2; s <= 4; ++s)
       if (nkb % s == 0 && nkb / s >= 4 && ctas * s <= slots) best = s;
     return best;
   }
@@ -925,8 +921,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   // the whole grid must be resident at once.  MSD_ATTN_MERGE=0 forces the combine kernel.
   const char* merge_env = getenv("MSD_ATTN_MERGE");
   const bool merge_allowed = !(merge_env && merge_env[0] == '0');
-  d.merge = (bkv == 64 && splits > 1 && splits <= 4 && a.flags != nullptr && merge_allowed &&
-             ctas * splits <= slots_bkv64()) ? 1 : 0;   // the owner keeps <= 3 partners in registers
+  d.merge = (splits > 1 && a.flags != nullptr && merge_allowed &&
+             ctas * splits <= (bkv == 64 ? slots_bkv64() : device_sm_count())) ? 1 : 0;
   int tail = 0;
   if (bkv == 128 && splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr &&
       a.tail >= 0)

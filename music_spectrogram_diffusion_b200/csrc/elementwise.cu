@@ -235,14 +235,20 @@ __device__ __forceinline__ float4 jax_normal4(const uint32_t* key, long long n, 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void sampler_step_body(const SamplerArgs& a, int step,
                                                   const float* noise_base, float* mel_base,
-                                                  unsigned long long seed, long long i4) {
+                                                  unsigned long long seed, long long i4,
+                                                  const float* eps_cond = nullptr,
+                                                  const float* eps_uncond = nullptr) {
   const long long idx = i4 * 4;
+  if (eps_cond == nullptr) {
+    eps_cond = a.eps;
+    eps_uncond = a.eps + a.n;
+  }
   const float* cf = a.coef + static_cast<size_t>(step) * MSD_STEP_COLS;
   const float x0_scale = cf[0], eps_scale = cf[1], c_z = cf[2], c_x0 = cf[3], sigma = cf[4];
   const bool last = cf[5] != 0.f;
   const float p0 = cf[8], p1 = cf[9], q0 = cf[10], q1 = cf[11], e1 = cf[12], e2 = cf[13];
   const float4 z = *reinterpret_cast<const float4*>(a.z + idx);
-  const float4 mo = *reinterpret_cast<const float4*>(a.eps + idx);
+  const float4 mo = *reinterpret_cast<const float4*>(eps_cond + idx);
   // _get_x0_and_eps_from_model_output (diffusion_utils.py:288-321): eps = p0 z + p1 out and
   // x0 = q0 z + q1 out (for model_output == 'eps': p0 = 0, p1 = 1, i.e. eps = out exactly)
   float4 e, x0;
@@ -251,7 +257,7 @@ __device__ __forceinline__ void sampler_step_body(const SamplerArgs& a, int step
   if (p0 == 0.f && p1 == 1.f) e = mo;
   if (a.passes == 2) {
     // classifier-free guidance on eps, then x0 from the combined eps at logsnr_t (424-433)
-    const float4 mu = *reinterpret_cast<const float4*>(a.eps + a.n + idx);
+    const float4 mu = *reinterpret_cast<const float4*>(eps_uncond + idx);
     float4 eu;
     eu.x = fmaf(p1, mu.x, p0 * z.x); eu.y = fmaf(p1, mu.y, p0 * z.y);
     eu.z = fmaf(p1, mu.z, p0 * z.z); eu.w = fmaf(p1, mu.w, p0 * z.w);
@@ -314,12 +320,23 @@ __device__ __forceinline__ void sampler_step_body(const SamplerArgs& a, int step
   }
 }
 
+__device__ __forceinline__ void prefetch_next_film(const SamplerArgs& a, int step, long long gid) {
+  if (a.film == nullptr || step < 1) return;
+  const long long off = gid * 32;  // one 128-byte line per thread
+  if (off < a.film_step_floats) {
+    const float* ptr = a.film + static_cast<long long>(step - 1) * a.film_step_floats + off;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+  }
+}
+
 __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) {
   griddep_launch_dependents();
   const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   griddep_wait();
   if (a.run == nullptr) {
-    if (i4 * 4 < a.n) sampler_step_body(a, *a.step, a.noise, a.mel_out, a.seed, i4);
+    const int step = *a.step;
+    prefetch_next_film(a, step, i4);
+    if (i4 * 4 < a.n) sampler_step_body(a, step, a.noise, a.mel_out, a.seed, i4);
     return;
   }
   // Per-call arguments and the step index live in device memory (RunArgs).  The step advance is
@@ -340,9 +357,48 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) 
   }
   __syncthreads();
   const int step = s_step;
+  prefetch_next_film(a, step, i4);
   const float* noise_base = a.run->noise;
   float* mel_base = a.run->mel_out;
   const unsigned long long seed = a.run->seed;
+  if (a.xrole != 0) {
+    // ---- guidance split: send my pass's eps to the peer, receive the peer's
+    __shared__ unsigned int s_seq;
+    if (threadIdx.x == 0) s_seq = *reinterpret_cast<volatile unsigned int*>(&a.run->xseq);
+    __syncthreads();
+    const unsigned int seq = s_seq;
+    const long long par = static_cast<long long>(seq & 1u) * a.xparity_floats;
+    if (i4 * 4 < a.n)
+      *reinterpret_cast<float4*>(a.xpeer + par + i4 * 4) = *reinterpret_cast<const float4*>(a.eps + i4 * 4);
+    __threadfence_system();   // my stores are visible to the peer before the flag is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(&a.run->xsent, 1u);
+      if (prev == gridDim.x - 1) {   // every block's share is on its way: raise the peer's flag
+        a.run->xsent = 0u;
+        a.run->xseq = seq + 1u;
+        unsigned int* pflag = reinterpret_cast<unsigned int*>(a.xpeer + a.xflags_off) + (seq & 1u);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pflag), "r"(seq) : "memory");
+      }
+      // wait for the peer's values of this step
+      const unsigned int* lflag = reinterpret_cast<const unsigned int*>(a.xlocal + a.xflags_off) + (seq & 1u);
+      unsigned int v;
+      unsigned long long spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lflag) : "memory");
+        if (v != seq) {
+          __nanosleep(200);
+          if (++spins > (1ull << 26)) __trap();   // ~15 s: the peer is gone, fail loudly
+        }
+      } while (v != seq);
+    }
+    __syncthreads();
+    const float* other = a.xlocal + par;
+    const float* ec = a.xrole == 1 ? a.eps : other;
+    const float* eu = a.xrole == 1 ? other : a.eps;
+    if (i4 * 4 < a.n) sampler_step_body(a, step, noise_base, mel_base, seed, i4, ec, eu);
+    return;
+  }
   if (i4 * 4 < a.n) sampler_step_body(a, step, noise_base, mel_base, seed, i4);
 }
 

@@ -237,6 +237,14 @@ struct msd_ctx {
   RunArgs* run = nullptr;         // per-call arguments + step index, device memory
   int* d_step = nullptr;          // == &run->step
 
+  // ---- classifier-free guidance split over two GPUs (msd_p2p_*): exchange buffer of this GPU
+  // ([2 parities][Bmax*N*nd] eps values + flag words; the peer writes into it) and the peer's,
+  // mapped through CUDA IPC
+  float* xchg = nullptr;
+  float* xchg_peer = nullptr;
+  int xrole = 0;                    // 0 off, 1 this GPU runs the conditional pass, 2 the unconditional
+  unsigned long long xcalls = 0;    // msd_sample calls since the attach (same on both ranks)
+
   int cur_batch = 0;
   // per-step graph: depends on the batch size only (noise / output / seed / step live in `run`)
   cudaGraphExec_t graph_exec = nullptr;
@@ -836,6 +844,14 @@ static int sampler_step(msd_ctx* c, int B, const float* noise, unsigned long lon
   a.clip_x0 = c->cfg.clip_x0; a.ddim = c->cfg.sampler == 1; a.feat_min = c->cfg.feature_min; a.feat_max = c->cfg.feature_max;
   a.seed = seed; a.rng_kind = c->cfg.rng_kind; a.rng_keys = c->rng_keys;
   a.run = use_run ? c->run : nullptr;
+  a.film = c->film;
+  a.film_step_floats = static_cast<long long>(2) * c->cfg.num_decoder_layers * 2 * c->d;
+  if (use_run && c->xrole != 0) {
+    a.passes = 2;   // both passes exist, one of them on the peer GPU
+    a.xrole = c->xrole; a.xlocal = c->xchg; a.xpeer = c->xchg_peer;
+    a.xparity_floats = static_cast<long long>(c->Bmax) * c->N * c->nd;
+    a.xflags_off = 2 * a.xparity_floats;
+  }
   return launch_sampler_step(a, st);
 }
 
@@ -998,6 +1014,15 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
       break;
     }
     c->d_step = &c->run->step;
+    {
+      const size_t xf = 2 * BN * c->nd + 64;
+      if ((rc = A.alloc(&c->xchg, xf))) break;
+      if (cudaMemset(c->xchg, 0, xf * sizeof(float)) != cudaSuccess) {
+        set_error("msd_create: cudaMemset failed");
+        rc = -2;
+        break;
+      }
+    }
     if ((rc = A.alloc(&c->coef, static_cast<size_t>(cfg->num_steps) * MSD_STEP_COLS))) break;
     if ((rc = A.alloc(&c->rng_keys, (static_cast<size_t>(cfg->num_steps) + 1) * 2))) break;
     if (cudaMemset(c->rng_keys, 0, (static_cast<size_t>(cfg->num_steps) + 1) * 2 * sizeof(uint32_t)) !=
@@ -1026,6 +1051,7 @@ void msd_destroy(msd_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   drop_graph(c);
+  if (c->xchg_peer) cudaIpcCloseMemHandle(c->xchg_peer);
   c->arena.release();
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
@@ -1189,6 +1215,11 @@ int msd_sample(msd_ctx* c, const float* init_z, const float* noise, uint64_t see
   // there, so neither a new noise tensor / output buffer / seed nor the step forces a re-capture.
   RunArgs ra;
   ra.noise = noise; ra.mel_out = mel_out; ra.seed = seed; ra.step = steps - 1; ra.done = 0u;
+  // guidance split: exchange sequence numbers 1, 2, ... identical on both ranks (they make the same
+  // calls), parity = buffer half
+  ra.xseq = static_cast<unsigned int>(c->xcalls * static_cast<unsigned long long>(steps) + 1ull);
+  ra.xsent = 0u;
+  if (c->xrole != 0) ++c->xcalls;
   MSD_CUDA_CHECK(cudaMemcpyAsync(c->run, &ra, sizeof(ra), cudaMemcpyHostToDevice, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));  // `ra` is a stack variable
   // One diffusion step == one graph launch; the same executable graph serves all num_steps
@@ -1198,7 +1229,8 @@ int msd_sample(msd_ctx* c, const float* init_z, const float* noise, uint64_t see
     const unsigned long long before = g_launch_count;
     cudaGraph_t graph = nullptr;
     MSD_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = run_decoder(c, B, B, c->passes * B, st, c->two_streams);
+    int rc = c->xrole == 0 ? run_decoder(c, B, B, c->passes * B, st, c->two_streams)
+                           : run_decoder(c, B, c->xrole == 1 ? B : 0, B, st, false);
     if (rc == 0) rc = sampler_step(c, B, nullptr, 0, nullptr, st, true);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != 0) {
@@ -1218,6 +1250,48 @@ int msd_sample(msd_ctx* c, const float* init_z, const float* noise, uint64_t see
     g_launch_count += c->graph_nodes;
   }
   MSD_TRY(end_on(c, caller));
+  return 0;
+}
+
+int msd_p2p_export(msd_ctx* c, void* handle_out) {
+  MSD_REQUIRE(c && handle_out, "msd_p2p_export: null argument");
+  MSD_CUDA_CHECK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  MSD_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->xchg));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int msd_p2p_attach(msd_ctx* c, const void* peer_handle, int32_t role) {
+  MSD_REQUIRE(c && peer_handle, "msd_p2p_attach: null argument");
+  MSD_REQUIRE(role == 1 || role == 2, "msd_p2p_attach: role must be 1 (conditional pass) or 2 (unconditional)");
+  MSD_REQUIRE(c->passes == 2, "msd_p2p_attach: guidance is off (eval_condition_weight == 1): nothing to split");
+  MSD_REQUIRE(c->xchg_peer == nullptr, "msd_p2p_attach: already attached; call msd_p2p_detach first");
+  MSD_CUDA_CHECK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, peer_handle, sizeof(h));
+  void* peer = nullptr;
+  MSD_CUDA_CHECK(cudaIpcOpenMemHandle(&peer, h, cudaIpcMemLazyEnablePeerAccess));
+  MSD_CUDA_CHECK(cudaStreamSynchronize(c->work));
+  // both ranks start from a clean slate: flags and sequence numbers restart at this point
+  const size_t xf = 2 * static_cast<size_t>(c->Bmax) * c->N * c->nd + 64;
+  MSD_CUDA_CHECK(cudaMemset(c->xchg, 0, xf * sizeof(float)));
+  c->xchg_peer = static_cast<float*>(peer);
+  c->xrole = role;
+  c->xcalls = 0;
+  drop_graph(c);
+  return 0;
+}
+
+int msd_p2p_detach(msd_ctx* c) {
+  MSD_REQUIRE(c != nullptr, "msd_p2p_detach: null argument");
+  MSD_CUDA_CHECK(cudaSetDevice(c->device));
+  MSD_CUDA_CHECK(cudaStreamSynchronize(c->work));
+  if (c->xchg_peer) MSD_CUDA_CHECK(cudaIpcCloseMemHandle(c->xchg_peer));
+  c->xchg_peer = nullptr;
+  c->xrole = 0;
+  drop_graph(c);
   return 0;
 }
 

@@ -169,6 +169,10 @@ struct RunArgs {
   unsigned long long seed;   // Philox stream (rng_kind 0)
   int step;                  // current reverse-step index i (decremented by the sampler kernel)
   unsigned int done;         // sampler blocks that have finished reading `step` (kept at 0)
+  // guidance split across two GPUs: sequence number of the NEXT exchange (identical on both
+  // ranks; advanced by the sampler kernel) and the counter of blocks that have sent their share
+  unsigned int xseq;
+  unsigned int xsent;
 };
 struct SamplerArgs {
   const float* eps;       // [(passes*B)*N, n_dims] rows: cond block then uncond block
@@ -193,6 +197,21 @@ struct SamplerArgs {
   // when non-null: noise / mel_out / seed / step are read from here (device memory) instead of the
   // fields above, and the last block to finish decrements run->step (the step advance)
   RunArgs* run;
+  // FiLM table [num_steps][film_step_floats]: the rows of the NEXT step (147 KB for base) are
+  // prefetched into L2 here, so that the 24 norm kernels of the next step do not each wait for
+  // HBM (the table is 147 MB, every row is read once per call)
+  const float* film; long long film_step_floats;
+  // Classifier-free guidance split over two GPUs (BASELINE config 5): this GPU ran
+  // ONE of the two decoder passes (xrole 1: the conditional one, 2: the unconditional one) and
+  // `eps` holds its n values.  The kernel stores them into the peer GPU's exchange buffer with
+  // plain st.global over NVLink (peer mapping of the other process's allocation), raises the
+  // peer's flag, waits for the peer's values in its own buffer and then does the update both
+  // GPUs need -- a fused compute + exchange kernel, no NCCL call in the loop.  Exchange buffer
+  // layout (floats): [2 parities][n] values, then 2 flag words at xflags_off.
+  int xrole;
+  float* xlocal;        // this GPU's buffer (the peer writes into it)
+  float* xpeer;         // the peer's buffer, mapped into this process
+  long long xparity_floats, xflags_off;
 };
 int launch_sampler_step(const SamplerArgs& a, cudaStream_t stream);
 

@@ -10,6 +10,12 @@ Two partitionings of the reference's serve path:
     GPU-to-GPU with send/recv (NCCL over NVLink on a B200 box, gloo in the CPU tests) instead of
     through host numpy; it does not (cannot) make one song faster than one GPU's batch-1 speed,
     it removes the host round trip and frees the other ranks for other songs.
+  * one song, faster (config 5): `CfgSplitPair` runs the conditional decoder pass
+    of every reverse step on one GPU and the unconditional pass on a second one; the two sampler
+    kernels swap their 128 KB of predicted noise per step by direct NVLink stores + a flag word
+    (msd_p2p_*: no NCCL call inside the loop) and apply the identical update, so both ranks hold
+    the same mel and the chain needs no hand-off at all.  torch.distributed only carries the two
+    64-byte IPC handles at set-up.
 The functions take a `predict_fn(tokens, ctx, ctx_mask, seed) -> mel` so the protocol is
 testable on CPU with gloo and a stand-in predict function.
 """
@@ -112,3 +118,66 @@ def synthesize_song(predict_fn: PredictFn, token_segments: Sequence[torch.Tensor
   for k, p in mine:
     dist.send(p.contiguous(), dst=0, group=group)
   return None
+
+
+class CfgSplitPair:
+  """Ranks `cond_rank` and `uncond_rank` of `group` share every reverse step of their (identical)
+  predict calls: one runs the conditional decoder pass, the other the unconditional one, and the
+  sampler kernels exchange the predicted noise GPU-to-GPU (engine.Engine.p2p_*).  Use as a context
+  manager around the chained-song loop; other ranks of the group are not involved."""
+
+  def __init__(self, model, cond_rank: int = 0, uncond_rank: int = 1,
+               group: Optional[dist.ProcessGroup] = None):
+    self.model, self.group = model, group
+    self.rank = dist.get_rank(group)
+    self.cond_rank, self.uncond_rank = cond_rank, uncond_rank
+    self.active = self.rank in (cond_rank, uncond_rank)
+
+  def __enter__(self):
+    handles: List[Optional[bytes]] = [None] * dist.get_world_size(self.group)
+    mine = self.model.engine.p2p_export() if self.active else b''
+    dist.all_gather_object(handles, mine, group=self.group)
+    if self.active:
+      peer = self.uncond_rank if self.rank == self.cond_rank else self.cond_rank
+      self.model.engine.p2p_attach(handles[peer], 'cond' if self.rank == self.cond_rank else 'uncond')
+    dist.barrier(group=self.group)   # nobody samples before both sides are attached
+    return self
+
+  def __exit__(self, *exc):
+    if self.active:
+      torch.cuda.synchronize(self.model.engine.device)
+    dist.barrier(group=self.group)   # both sides are done with each other's buffer
+    if self.active:
+      self.model.engine.p2p_detach()
+    return False
+
+
+def synthesize_song_cfg_split(model, token_segments: Sequence[torch.Tensor], context_frames: int,
+                              n_dims: int, seed: int = 0, always_mask_context: bool = False,
+                              group: Optional[dist.ProcessGroup] = None,
+                              timings: Optional[List[float]] = None) -> Optional[torch.Tensor]:
+  """One chained song (InferSong.process, beam/evaluation.py:156-223) on ranks 0 and 1 of `group`
+  with the guidance split; every other rank returns None at once.  Both participating ranks
+  return the full mel [1, n_segments * frames, n_dims] (they compute identical copies).  When
+  `timings` is given, the wall seconds of every segment but the first are appended (the
+  reference's model_timing protocol, evaluation.py:217-220)."""
+  import time
+  rank = dist.get_rank(group)
+  with CfgSplitPair(model, 0, 1, group) as pair:
+    if not pair.active:
+      return None
+    device = model.engine.device
+    prev = torch.zeros(1, context_frames, n_dims, dtype=torch.float32, device=device)
+    outs = []
+    for k, toks in enumerate(token_segments):
+      first = (k == 0) or always_mask_context
+      mask = (torch.zeros if first else torch.ones)(1, context_frames, dtype=torch.int32, device=device)
+      torch.cuda.synchronize(device)
+      tick = time.time()
+      pred = model.predict_on_device(toks.to(device).reshape(1, -1), prev, mask, seed)
+      torch.cuda.synchronize(device)
+      if timings is not None and k > 0:
+        timings.append(time.time() - tick)
+      outs.append(pred)
+      prev = pred[:1]
+    return torch.cat(outs, dim=1)

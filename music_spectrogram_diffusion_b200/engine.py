@@ -184,6 +184,23 @@ class Engine:
                                       _stream(self.device)), 'msd_sample')
     return out
 
+  # -- guidance split over two GPUs (msd_p2p_*, include/msd_b200.h) --------------------------
+  def p2p_export(self) -> bytes:
+    buf = ctypes.create_string_buffer(64)
+    _native.check(self.lib.msd_p2p_export(self._h, buf), 'msd_p2p_export')
+    return buf.raw
+
+  def p2p_attach(self, peer_handle: bytes, role: str) -> None:
+    """role: 'cond' (this GPU runs the conditional pass) or 'uncond'."""
+    if len(peer_handle) != 64:
+      raise ValueError('peer handle must be the 64 bytes msd_p2p_export returned on the other rank')
+    self._peer_handle = ctypes.create_string_buffer(peer_handle, 64)
+    _native.check(self.lib.msd_p2p_attach(self._h, self._peer_handle,
+                                          {'cond': 1, 'uncond': 2}[role]), 'msd_p2p_attach')
+
+  def p2p_detach(self) -> None:
+    _native.check(self.lib.msd_p2p_detach(self._h), 'msd_p2p_detach')
+
   KERNEL_CLASSES = ('gemm', 'attention', 'rmsnorm_film', 'sampler', 'other')
 
   def profile_step(self, step_i: int = 500, reps: int = 3) -> Dict[str, Dict[str, float]]:

@@ -93,3 +93,64 @@ def test_two_ranks_match_single_process():
     np.testing.assert_array_equal(want_song[0, k * FRAMES:(k + 1) * FRAMES].numpy(), prev[0].numpy())
   # the chain really chains: segment 1 depends on segment 0's output
   assert not np.allclose(want_song[0, :FRAMES].numpy(), want_song[0, FRAMES:2 * FRAMES].numpy())
+
+
+class _FakeEngine:
+  """Stands in for engine.Engine in the guidance-split set-up protocol."""
+
+  def __init__(self, rank):
+    self.rank, self.attached, self.device = rank, None, torch.device('cpu')
+
+  def p2p_export(self):
+    return bytes([self.rank]) * 64
+
+  def p2p_attach(self, handle, role):
+    assert len(handle) == 64
+    self.attached = (handle[0], role)
+
+  def p2p_detach(self):
+    self.attached = None
+
+
+class _FakeModel:
+  def __init__(self, rank):
+    self.engine = _FakeEngine(rank)
+
+
+def _pair_worker(rank, world, port, q):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  model = _FakeModel(rank)
+  orig_sync = torch.cuda.synchronize
+  torch.cuda.synchronize = lambda *a, **k: None   # CPU stand-in
+  try:
+    with D.CfgSplitPair(model, 0, 1) as pair:
+      inside = (pair.active, model.engine.attached)
+    q.put((rank, inside, model.engine.attached))
+  finally:
+    torch.cuda.synchronize = orig_sync
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_guidance_split_pairing_protocol():
+  """CfgSplitPair: ranks 0 / 1 swap their 64-byte handles and attach with roles cond / uncond,
+  a third rank takes part in the barriers only; everybody detaches on exit."""
+  world = 3
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_pair_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  res = {}
+  for _ in range(world):
+    r, inside, after = q.get(timeout=120)
+    res[r] = (inside, after)
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  assert res[0] == ((True, (1, 'cond')), None)      # rank 0 holds rank 1's handle, conditional pass
+  assert res[1] == ((True, (0, 'uncond')), None)
+  assert res[2] == ((False, None), None)
