@@ -921,7 +921,11 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   // the whole grid must be resident at once.  MSD_ATTN_MERGE=0 forces the combine kernel.
   const char* merge_env = getenv("MSD_ATTN_MERGE");
   const bool merge_allowed = !(merge_env && merge_env[0] == '0');
-  d.merge = (splits > 1 && a.flags != nullptr && merge_allowed &&
+  // Default: only with the 64-key instance (few partners, all CTAs resident).  For the small
+  // grids of one segment (128-key instance, 6 splits) the owner's wait + serial merge measured
+  // slower than the combine kernel (batch-1 step 1035 vs 977 us); MSD_ATTN_MERGE=2 forces it.
+  const bool merge_forced = merge_env && merge_env[0] == '2';
+  d.merge = (splits > 1 && a.flags != nullptr && merge_allowed && (bkv == 64 || merge_forced) &&
              ctas * splits <= (bkv == 64 ? slots_bkv64() : device_sm_count())) ? 1 : 0;
   int tail = 0;
   if (bkv == 128 && splits == 1 && a.flags != nullptr && a.part_o != nullptr && a.part_ml != nullptr &&

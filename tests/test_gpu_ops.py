@@ -86,7 +86,7 @@ def test_dot_product_attention(cuda_device, monkeypatch, nb, heads, Lq, Lk, mask
   if splits == 1 and merge == 0:
     pytest.skip('same launch as merge=1')
   monkeypatch.setenv('MSD_ATTN_BKV', str(bkv))
-  monkeypatch.setenv('MSD_ATTN_MERGE', str(merge))
+  monkeypatch.setenv('MSD_ATTN_MERGE', '0' if merge == 0 else ('2' if bkv == 128 else '1'))
   if splits:
     monkeypatch.setenv('MSD_ATTN_SPLITS', str(splits))
   g = torch.Generator().manual_seed(nb * 1000 + Lk)
