@@ -7,6 +7,12 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#define MSD_TRY_RC(expr)      \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
 namespace msd {
 
 std::atomic<unsigned long long> g_launch_count{0};
@@ -40,32 +46,45 @@ struct NormDev {
 
 constexpr int NORM_MAX_ITERS = 8;  // d <= 1024
 
+// ITERS = d / 128 (float4 per lane), a template parameter so that the per-row constants (gamma
+// and the FiLM scale | bias rows) can be requested together with the row itself: their L2 round
+// trip then overlaps the row's instead of following the warp reduction (the kernel is a pure
+// latency chain: ~5 us for 19 MB of traffic).
+template <int ITERS>
 __global__ void __launch_bounds__(256) rmsnorm_film_kernel(const NormDev p) {
   griddep_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= p.rows) return;
-  griddep_wait();
-  const int iters = p.d >> 7;  // float4 per lane
-  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(warp) * p.d);
-  float4 v[NORM_MAX_ITERS];
-  float ss = 0.f;
+  constexpr int D = ITERS * 128;
+  // per-segment constants: safe to read ahead of the dependency wait (written at load time)
+  float4 g[ITERS];
 #pragma unroll
-  for (int i = 0; i < NORM_MAX_ITERS; ++i) {
-    if (i < iters) {
-      v[i] = xr[i * 32 + lane];
-      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  for (int i = 0; i < ITERS; ++i)
+    g[i] = __ldg(reinterpret_cast<const float4*>(p.gamma + (i * 32 + lane) * 4));
+  griddep_wait();
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(warp) * D);
+  float4 v[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) v[i] = xr[i * 32 + lane];
+  float4 fsv[ITERS], fbv[ITERS];
+  const bool has_film = p.film != nullptr;
+  if (has_film) {
+    const long long base = static_cast<long long>(*p.step) * p.film_step_stride + p.film_offset;
+    const float* fs = p.film + base;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      fsv[i] = __ldg(reinterpret_cast<const float4*>(fs + c));
+      fbv[i] = __ldg(reinterpret_cast<const float4*>(fs + D + c));
     }
   }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i)
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   ss = warp_sum(ss);
-  const float inv = rsqrtf(ss / static_cast<float>(p.d) + 1e-6f);
-  const float* fs = nullptr;
-  const float* fb = nullptr;
-  if (p.film != nullptr) {
-    const long long base = static_cast<long long>(*p.step) * p.film_step_stride + p.film_offset;
-    fs = p.film + base;
-    fb = fs + p.d;
-  }
+  const float inv = rsqrtf(ss / static_cast<float>(D) + 1e-6f);
   int orow = warp;
   if (p.src_len > 0) {
     const int b = warp / p.src_len;
@@ -73,37 +92,55 @@ __global__ void __launch_bounds__(256) rmsnorm_film_kernel(const NormDev p) {
   }
   bf16* o = p.out + static_cast<size_t>(orow) * p.ldo;
 #pragma unroll
-  for (int i = 0; i < NORM_MAX_ITERS; ++i) {
-    if (i < iters) {
-      const int c = (i * 32 + lane) * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
-      float y0 = v[i].x * inv * g.x, y1 = v[i].y * inv * g.y;
-      float y2 = v[i].z * inv * g.z, y3 = v[i].w * inv * g.w;
-      if (fs != nullptr) {
-        const float4 s = __ldg(reinterpret_cast<const float4*>(fs + c));
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(fb + c));
-        y0 = y0 * (s.x + 1.0f) + bb.x; y1 = y1 * (s.y + 1.0f) + bb.y;
-        y2 = y2 * (s.z + 1.0f) + bb.z; y3 = y3 * (s.w + 1.0f) + bb.w;
-      }
-      if (!p.split3) {
-        uint2 u;
-        u.x = pack_bf16(y0, y1);
-        u.y = pack_bf16(y2, y3);
-        *reinterpret_cast<uint2*>(o + c) = u;
-      } else {
-        bf16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(y0, h0, l0); split_bf16(y1, h1, l1);
-        split_bf16(y2, h2, l2); split_bf16(y3, h3, l3);
-        __nv_bfloat162 a = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
-        __nv_bfloat162 c0 = __halves2bfloat162(l0, l1), c1 = __halves2bfloat162(l2, l3);
-        uint2 uh, ul;
-        uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b2);
-        ul.x = *reinterpret_cast<uint32_t*>(&c0); ul.y = *reinterpret_cast<uint32_t*>(&c1);
-        *reinterpret_cast<uint2*>(o + c) = uh;              // hi
-        *reinterpret_cast<uint2*>(o + p.d + c) = ul;        // lo
-        *reinterpret_cast<uint2*>(o + 2 * p.d + c) = uh;    // hi
-      }
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float y0 = v[i].x * inv * g[i].x, y1 = v[i].y * inv * g[i].y;
+    float y2 = v[i].z * inv * g[i].z, y3 = v[i].w * inv * g[i].w;
+    if (has_film) {
+      y0 = y0 * (fsv[i].x + 1.0f) + fbv[i].x; y1 = y1 * (fsv[i].y + 1.0f) + fbv[i].y;
+      y2 = y2 * (fsv[i].z + 1.0f) + fbv[i].z; y3 = y3 * (fsv[i].w + 1.0f) + fbv[i].w;
     }
+    if (!p.split3) {
+      uint2 u;
+      u.x = pack_bf16(y0, y1);
+      u.y = pack_bf16(y2, y3);
+      *reinterpret_cast<uint2*>(o + c) = u;
+    } else {
+      bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(y0, h0, l0); split_bf16(y1, h1, l1);
+      split_bf16(y2, h2, l2); split_bf16(y3, h3, l3);
+      __nv_bfloat162 a = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
+      __nv_bfloat162 c0 = __halves2bfloat162(l0, l1), c1 = __halves2bfloat162(l2, l3);
+      uint2 uh, ul;
+      uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b2);
+      ul.x = *reinterpret_cast<uint32_t*>(&c0); ul.y = *reinterpret_cast<uint32_t*>(&c1);
+      *reinterpret_cast<uint2*>(o + c) = uh;            // hi
+      *reinterpret_cast<uint2*>(o + D + c) = ul;        // lo
+      *reinterpret_cast<uint2*>(o + 2 * D + c) = uh;    // hi
+    }
+  }
+}
+
+template <int ITERS>
+int launch_norm_iters(const NormDev& p, cudaStream_t stream) {
+  static const int configured = [] {
+    return cudaFuncSetAttribute(rmsnorm_film_kernel<ITERS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                100) == cudaSuccess ? 0 : -2;
+  }();
+  MSD_REQUIRE(configured == 0, "rmsnorm: cudaFuncSetAttribute failed");
+  MSD_CUDA_CHECK(launch_kernel(rmsnorm_film_kernel<ITERS>, dim3((p.rows + 7) / 8), dim3(256), 0, stream, p));
+  return 0;
+}
+int launch_norm(const NormDev& p, cudaStream_t stream) {
+  switch (p.d >> 7) {
+    case 1: return launch_norm_iters<1>(p, stream);
+    case 2: return launch_norm_iters<2>(p, stream);
+    case 3: return launch_norm_iters<3>(p, stream);
+    case 4: return launch_norm_iters<4>(p, stream);
+    case 5: return launch_norm_iters<5>(p, stream);
+    case 6: return launch_norm_iters<6>(p, stream);
+    case 7: return launch_norm_iters<7>(p, stream);
+    default: return launch_norm_iters<8>(p, stream);
   }
 }
 
@@ -605,8 +642,6 @@ inline int blocks_for(long long n, int per_block) {
 // ones that use no shared memory: alternating carve-outs between consecutive kernels forces an SM
 // reconfiguration (the SM must drain first), which also defeats programmatic dependent launch.
 int elementwise_configure() {
-  MSD_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_film_kernel,
-                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   MSD_CUDA_CHECK(cudaFuncSetAttribute(sampler_step_kernel,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   MSD_CUDA_CHECK(cudaFuncSetAttribute(init_z_kernel,
@@ -624,7 +659,7 @@ int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* ou
   p.rows = rows; p.d = d; p.ldo = ldo; p.split3 = split3;
   p.src_len = 0; p.dst_len = 0; p.dst_off = 0;
   ProfScope prof(KC_NORM, 0.0, static_cast<double>(rows) * d * (4.0 + (split3 ? 6.0 : 2.0)), stream);
-  MSD_CUDA_CHECK(launch_kernel(rmsnorm_film_kernel, dim3(blocks_for(rows, 8)), dim3(256), 0, stream, p));
+  MSD_TRY_RC(launch_norm(p, stream));
   ++g_launch_count;
   return 0;
 }
@@ -638,7 +673,7 @@ int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src
   p.film_step_stride = 0; p.film_offset = 0;
   p.rows = B * src_len; p.d = d; p.ldo = split3 ? 3 * d : d; p.split3 = split3;
   p.src_len = src_len; p.dst_len = dst_len; p.dst_off = dst_off;
-  MSD_CUDA_CHECK(launch_kernel(rmsnorm_film_kernel, dim3(blocks_for(p.rows, 8)), dim3(256), 0, stream, p));
+  MSD_TRY_RC(launch_norm(p, stream));
   ++g_launch_count;
   return 0;
 }
