@@ -33,8 +33,8 @@ from typing import Any, Dict, Mapping, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from music_spectrogram_diffusion_b200 import (audio_codecs, config, engine, gin_lite, t5x_checkpoint,
-                                              weights)
+from music_spectrogram_diffusion_b200 import (audio_codecs, config, engine, gin_lite, midi_tokens,
+                                              t5x_checkpoint, weights)
 
 _GIN_SEARCH_ROOTS = [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))]
 
@@ -80,41 +80,33 @@ class _Partitioner:
     return fn
 
 
-@dataclasses.dataclass
-class EventCodecInfo:
-  """Sizes of `vocabularies.build_codec` (msd/vocabularies.py:118-144; event_codec.py:64-66).
-  The MIDI tokeniser itself is outside this path."""
-  steps_per_second: int = 100
-  max_shift_steps: int = 1000
-  num_velocity_bins: int = 127
-
-  @property
-  def num_classes(self) -> int:
-    # shift [0, max] + pitch 128 + velocity [0, bins] + tie 1 + program 128 + drum 128
-    return (self.max_shift_steps + 1) + 128 + (self.num_velocity_bins + 1) + 1 + 128 + 128
+def build_codec(num_velocity_bins: int = 127, steps_per_second: int = 100,
+                max_shift_seconds: int = 10) -> midi_tokens.EventVocabulary:
+  """vocabularies.build_codec (msd/vocabularies.py:118-144): the event codec of a
+  VocabularyConfig -- shift [0, max], pitch 128, velocity [0, bins], tie 1, program 128, drum 128.
+  The same object `midi_tokens` tokenises with (one vocabulary implementation, not two)."""
+  return midi_tokens.mt3_event_vocabulary(midi_tokens.VocabularyConfig(
+      steps_per_second=steps_per_second, max_shift_seconds=max_shift_seconds,
+      num_velocity_bins=num_velocity_bins))
 
 
-def num_embeddings(codec: EventCodecInfo, extra_ids: int = 100) -> int:
+def num_embeddings(codec: midi_tokens.EventVocabulary, extra_ids: int = 100) -> int:
   """vocabularies.num_embeddings (279-281): 3 specials + classes + extra ids, up to k*128."""
   vocab_size = 3 + codec.num_classes + extra_ids
   return 128 * math.ceil(vocab_size / 128)
 
 
 def _build_from_gin(gin_config: str) -> Tuple[config.T5Config, config.DiffusionConfig,
-                                              Dict[str, int], EventCodecInfo]:
+                                              Dict[str, int], midi_tokens.EventVocabulary]:
   g = gin_lite.parse_config(gin_config, _GIN_SEARCH_ROOTS)
   lengths = dict(g.query_macro('TASK_FEATURE_LENGTHS'))
 
   vb = g.bindings_for('vocabularies.VocabularyConfig')
-  codec = EventCodecInfo()
-  if 'num_velocity_bins' in vb:
-    codec.num_velocity_bins = int(g.resolve(vb['num_velocity_bins']))
-  if 'steps_per_second' in vb:
-    codec.steps_per_second = int(g.resolve(vb['steps_per_second']))
-  if 'max_shift_seconds' in vb:
-    codec.max_shift_steps = codec.steps_per_second * int(g.resolve(vb['max_shift_seconds']))
-  else:
-    codec.max_shift_steps = codec.steps_per_second * 10
+  kw = {}
+  for name in ('num_velocity_bins', 'steps_per_second', 'max_shift_seconds'):
+    if name in vb:
+      kw[name] = int(g.resolve(vb[name]))
+  codec = build_codec(**kw)
 
   t5 = config.T5Config()
   for k, v in g.bindings_for('network.T5Config').items():
@@ -177,7 +169,7 @@ class InferenceModel:
                   params: Optional[Dict[str, np.ndarray]] = None,
                   rng: str = 'jax', precision: str = 'bf16') -> 'InferenceModel':
     self = cls.__new__(cls)
-    self._init_common(checkpoint_path, t5, diffusion, dict(sequence_length), EventCodecInfo(),
+    self._init_common(checkpoint_path, t5, diffusion, dict(sequence_length), build_codec(),
                       batch_size, device, params, rng, precision)
     return self
 

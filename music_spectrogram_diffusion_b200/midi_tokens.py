@@ -110,6 +110,38 @@ class EventVocabulary:
       raise ValueError(f'Unknown event index: {index}')
     return self.kinds[s], int(self._lo[s] + index - self._base[s])
 
+  # ---- the method names of the reference's event_codec.Codec (event_codec.py:64-112), so that
+  # `InferenceModel.codec` can be used where callers expect that object (inference.py:110-111)
+  def is_shift_event_index(self, index: int) -> bool:
+    return self.is_shift(index)
+
+  def encode_event(self, event) -> int:
+    """event: anything with .type and .value (event_codec.Event) or a (type, value) pair."""
+    kind, value = (event.type, event.value) if hasattr(event, 'type') else event
+    return self.encode(kind, value)
+
+  def event_type_range(self, event_type: str) -> Tuple[int, int]:
+    return self.id_range(event_type)
+
+  def decode_event_index(self, index: int) -> 'Event':
+    return Event(*self.decode(index))
+
+  @property
+  def num_velocity_bins(self) -> int:
+    lo, hi = self.id_range('velocity')
+    return hi - lo
+
+  @property
+  def max_shift_seconds(self) -> int:
+    return int(round(self.max_shift_steps / self.steps_per_second))
+
+
+@dataclasses.dataclass(frozen=True)
+class Event:
+  """event_codec.Event (event_codec.py:28-31)."""
+  type: str
+  value: int
+
 
 @dataclasses.dataclass
 class VocabularyConfig:

@@ -18,12 +18,8 @@ from music_spectrogram_diffusion_b200 import midi_file, midi_tokens
 
 
 def event_vocabulary_of(model) -> midi_tokens.EventVocabulary:
-  """The model's event vocabulary from its gin VocabularyConfig (InferenceModel.codec)."""
-  c = model.codec
-  return midi_tokens.mt3_event_vocabulary(midi_tokens.VocabularyConfig(
-      steps_per_second=c.steps_per_second,
-      max_shift_seconds=c.max_shift_steps // c.steps_per_second,
-      num_velocity_bins=c.num_velocity_bins))
+  """The model's event vocabulary: `InferenceModel.codec` is the tokeniser's own object."""
+  return model.codec
 
 
 def load_notes(midi: Union[str, bytes], sustain: bool = True) -> np.ndarray:

@@ -73,9 +73,14 @@ def test_inference_model_config_surface(tmp_path):
 
 def test_vocab_size_rule():
   """vocabularies.py:118-144, 279-281: 1388 codec classes + 3 + 100 -> 1536."""
-  c = inference.EventCodecInfo(num_velocity_bins=1)
+  c = inference.build_codec(num_velocity_bins=1)
   assert c.num_classes == 1388 and inference.num_embeddings(c) == 1536
-  assert inference.num_embeddings(inference.EventCodecInfo(num_velocity_bins=127)) == 1664
+  assert inference.num_embeddings(inference.build_codec(num_velocity_bins=127)) == 1664
+  # the reference's Codec surface (event_codec.py:64-112) on the same object
+  assert c.max_shift_steps == 1000 and c.steps_per_second == 100 and c.is_shift_event_index(1000)
+  assert not c.is_shift_event_index(1001) and c.event_type_range('pitch') == (1001, 1128)
+  ev = c.decode_event_index(c.encode_event(('program', 40)))
+  assert (ev.type, ev.value) == ('program', 40)
 
 
 def test_unsupported_configs_fail_loudly():

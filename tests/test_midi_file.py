@@ -71,7 +71,7 @@ class _FakeModel:
   def __init__(self):
     from music_spectrogram_diffusion_b200 import audio_codecs, inference
     self.audio_codec = audio_codecs.MelGAN()
-    self.codec = inference.EventCodecInfo(num_velocity_bins=1)
+    self.codec = inference.build_codec(num_velocity_bins=1)
     self.sequence_length = {'inputs': 2048, 'targets': 256, 'targets_context': 256}
     self.calls = []
 
