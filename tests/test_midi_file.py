@@ -99,28 +99,3 @@ def test_song_driver_chains_context_like_the_colab_loop():
   v = song.event_vocabulary_of(m)
   assert list(m.calls[1]['encoder_input_tokens'][0, :3]) == [
       v.encode('program', 0) + 3, v.encode('pitch', 60) + 3, v.encode('tie', 0) + 3]
-
-
-def test_command_line_front_end(tmp_path, monkeypatch):
-  """python -m music_spectrogram_diffusion_b200.synthesize: MIDI in, .npy mel out (the engine is
-  replaced by the recording stand-in; the GPU path is covered by the gpu tests)."""
-  from music_spectrogram_diffusion_b200 import inference, synthesize
-  notes = M.make_notes([(0.0, 6.0, 60, 100, 0, False), (1.0, 1.5, 64, 80, 40, False)])
-  midi = tmp_path / 'tune.mid'
-  midi.write_bytes(F.write_midi(notes))
-  seen = {}
-
-  class Stub(_FakeModel):
-    def __init__(self, checkpoint_path, gin_config, batch_size=1, device=0):
-      super().__init__()
-      seen.update(checkpoint=checkpoint_path, gin=gin_config, batch=batch_size)
-
-  monkeypatch.setattr(inference, 'InferenceModel', Stub)
-  out = tmp_path / 'mel.npy'
-  rc = synthesize.main([str(midi), str(out), '--seed', '5', '--cond-weight', '3.5',
-                        '--gin-binding', "diffusion_utils.SamplerConfig.name = 'ddim'"])
-  assert rc == 0
-  mel = np.load(out)
-  assert mel.shape == (M.num_song_frames(6.0), 128) and mel.dtype == np.float32
-  assert seen['checkpoint'] == 'synthetic:0' and seen['batch'] == 1
-  assert 'eval_condition_weight = 3.5' in seen['gin'] and "SamplerConfig.name = 'ddim'" in seen['gin']
