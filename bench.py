@@ -327,12 +327,14 @@ def graph_timeline(eng, seed=2):
   except Exception as e:  # pylint: disable=broad-except
     return {'unavailable': f'{type(e).__name__}: {e}'}, None
   ev.sort(key=lambda e: e['ts'])
-  # a step = everything after one sampler_step kernel up to and including the next
-  ends = [i for i, e in enumerate(ev) if 'sampler_step' in e['name']]
-  if len(ends) < 4:
-    return {'unavailable': f'only {len(ends)} steps in the trace'}, None
-  lo, hi = ends[len(ends) // 2 - 1] + 1, ends[len(ends) // 2] + 1
-  step = ev[lo:hi]
+  # the call = a few set-up kernels (noise draw) + num_steps identical graph replays
+  steps = int(eng.cfg.num_steps)
+  pre = next((k for k in range(4) if (len(ev) - k) % steps == 0 and len(ev) > k), None)
+  if pre is None or steps < 4:
+    return {'unavailable': f'{len(ev)} kernels do not split into {steps} equal steps'}, None
+  nodes = (len(ev) - pre) // steps
+  lo = pre + (steps // 2) * nodes
+  step = ev[lo:lo + nodes]
   t0 = step[0]['ts']
   rows, crit, busy = [], {}, {}
   prev_end = t0
