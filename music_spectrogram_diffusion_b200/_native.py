@@ -20,7 +20,7 @@ LIB_NAME = 'libmsd_b200.so'
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 SOURCES = ['gemm_tcgen05.cu', 'attention_tcgen05.cu', 'attention_f32.cu', 'elementwise.cu',
            'engine.cu']
-HEADERS = ['common.cuh', 'kernels.h', 'sampler.cuh']
+HEADERS = ['common.cuh', 'kernels.h']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
     '-std=c++17', '-Xcompiler', '-fPIC',

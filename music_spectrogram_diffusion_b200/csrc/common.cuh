@@ -284,45 +284,6 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
                : "memory");
 }
 
-// ---- distributed shared memory between the two CTAs of a pair
-// shared::cluster address of `p` (an address in THIS CTA's shared memory) in CTA `rank`
-__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ float4 ld_cluster_f32x4(uint32_t cluster_addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(cluster_addr)
-               : "memory");
-  return v;
-}
-// arrive (count 1) on an mbarrier of another CTA of the cluster; orders this thread's earlier
-// writes (and, cumulatively, what it synchronised with) before the arrival at cluster scope
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
-}
-// wait on an mbarrier of this CTA for an arrival that came from another CTA of the cluster
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
-        : "memory");
-    if (ok) return;
-    if (++spins > MSD_MBAR_SPIN_LIMIT) __trap();
-  }
-}
-
 // TMEM -> registers: each thread reads 32 consecutive 32-bit columns of ITS lane
 // (lane = 32*(warp%4) + laneid).  taddr = (lane_base << 16) | column.
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {

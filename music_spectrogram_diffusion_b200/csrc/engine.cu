@@ -801,7 +801,7 @@ static int decoder_layers(msd_ctx* c, int seg0, int nseg, int ncross, cudaStream
 // combine -- run as two concurrent kernel chains (fork/join on c->work2); a measured-slower
 // experiment (MSD_TWO_STREAMS=1), see msd_create.
 static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st,
-                       bool two_streams = false, const SamplerArgs* fused_sampler = nullptr) {
+                       bool two_streams = false) {
   const int d = c->d, N = c->N, nd = c->nd;
   const int R = total * N;
   // continuous_inputs_projection + position encodings (420-427); both passes start equal.
@@ -827,23 +827,14 @@ static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st,
   }
   // decoder_norm + spec_out_dense in split precision (445-456: fp32 "for stability")
   MSD_TRY(launch_rmsnorm(c->x, c->dec_norm, R, d, c->xn, 3 * d, nullptr, nullptr, 0, 0, 1, st));
-  if (fused_sampler != nullptr) {
-    // the reverse-diffusion update runs in this GEMM's epilogue (EPI_SAMPLER): no eps round trip
-    // through memory, no separate sampler kernel
-    GemmArgs a;
-    memset(&a, 0, sizeof(a));
-    a.A = c->xn; a.B = c->spec_out; a.M = R; a.N = nd; a.K = 3 * d; a.lda = 3 * d; a.ldb = 3 * d;
-    a.epilogue = EPI_SAMPLER; a.sampler = fused_sampler;
-    return launch_gemm(a, st);
-  }
   MSD_TRY(gemm(c->xn, 3 * d, c->spec_out, 3 * d, R, nd, 3 * d, EPI_F32, c->eps, nd, nullptr, st));
   return 0;
 }
 
-// Arguments of one reverse-diffusion update.  With `use_run` the per-call arguments and the step
-// index are read from c->run (device memory) and the kernel also advances the step (graph path).
-static SamplerArgs make_sampler_args(msd_ctx* c, int B, const float* noise, unsigned long long seed,
-                                     float* mel_out, bool use_run) {
+// One reverse-diffusion update.  With `use_run` the per-call arguments and the step index are
+// read from c->run (device memory) and the kernel also advances the step (the graph path).
+static int sampler_step(msd_ctx* c, int B, const float* noise, unsigned long long seed,
+                        float* mel_out, cudaStream_t st, bool use_run) {
   SamplerArgs a;
   memset(&a, 0, sizeof(a));
   a.eps = c->eps; a.z = c->z; a.z_split = c->z_split; a.noise = noise; a.coef = c->coef;
@@ -861,19 +852,7 @@ static SamplerArgs make_sampler_args(msd_ctx* c, int B, const float* noise, unsi
     a.xparity_floats = static_cast<long long>(c->Bmax) * c->N * c->nd;
     a.xflags_off = 2 * a.xparity_floats;
   }
-  return a;
-}
-
-static int sampler_step(msd_ctx* c, int B, const float* noise, unsigned long long seed,
-                        float* mel_out, cudaStream_t st, bool use_run) {
-  return launch_sampler_step(make_sampler_args(c, B, noise, seed, mel_out, use_run), st);
-}
-
-// The update rides in the final projection's epilogue when both guidance passes run on this GPU
-// (MSD_FUSE_SAMPLER=0: separate kernel, for comparison).
-static bool fuse_sampler(const msd_ctx* c) {
-  const char* e = getenv("MSD_FUSE_SAMPLER");
-  return c->passes == 2 && c->xrole == 0 && !c->two_streams && !(e && e[0] == '0');
+  return launch_sampler_step(a, st);
 }
 
 
@@ -1250,15 +1229,9 @@ int msd_sample(msd_ctx* c, const float* init_z, const float* noise, uint64_t see
     const unsigned long long before = g_launch_count;
     cudaGraph_t graph = nullptr;
     MSD_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc;
-    if (fuse_sampler(c)) {
-      const SamplerArgs sa = make_sampler_args(c, B, nullptr, 0, nullptr, true);
-      rc = run_decoder(c, B, B, c->passes * B, st, false, &sa);
-    } else {
-      rc = c->xrole == 0 ? run_decoder(c, B, B, c->passes * B, st, c->two_streams)
-                         : run_decoder(c, B, c->xrole == 1 ? B : 0, B, st, false);
-      if (rc == 0) rc = sampler_step(c, B, nullptr, 0, nullptr, st, true);
-    }
+    int rc = c->xrole == 0 ? run_decoder(c, B, B, c->passes * B, st, c->two_streams)
+                           : run_decoder(c, B, c->xrole == 1 ? B : 0, B, st, false);
+    if (rc == 0) rc = sampler_step(c, B, nullptr, 0, nullptr, st, true);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != 0) {
       if (graph) cudaGraphDestroy(graph);
@@ -1333,22 +1306,14 @@ int msd_profile_step(msd_ctx* c, int32_t step_i, int32_t reps, double* out) {
   for (int i = 0; i < 4 * KC_COUNT; ++i) out[i] = 0.0;
   const unsigned long long before = g_launch_count;
   int rc = 0;
+  MSD_CUDA_CHECK(cudaMemcpyAsync(c->d_step, &step_i, sizeof(int), cudaMemcpyHostToDevice, st));
+  MSD_CUDA_CHECK(cudaStreamSynchronize(st));
   for (int r = 0; r < reps + 1 && rc == 0; ++r) {
     // repetition 0 is an untimed warm-up; z just keeps evolving, the work per step is identical
-    // (the same kernels as the captured step graph, fed from fresh device-resident run arguments)
-    RunArgs ra;
-    memset(&ra, 0, sizeof(ra));
-    ra.seed = 1234; ra.step = step_i;
-    MSD_CUDA_CHECK(cudaMemcpyAsync(c->run, &ra, sizeof(ra), cudaMemcpyHostToDevice, st));
-    MSD_CUDA_CHECK(cudaStreamSynchronize(st));
+    // (the same kernels as the captured step graph; the step index is simply not advanced)
     if (r == 1) g_prof = &rec;
-    if (fuse_sampler(c)) {
-      const SamplerArgs sa = make_sampler_args(c, B, nullptr, 1234, nullptr, true);
-      rc = run_decoder(c, B, B, c->passes * B, st, false, &sa);
-    } else {
-      rc = run_decoder(c, B, B, c->passes * B, st);
-      if (rc == 0) rc = sampler_step(c, B, nullptr, 1234, nullptr, st, true);
-    }
+    rc = run_decoder(c, B, B, c->passes * B, st);
+    if (rc == 0) rc = sampler_step(c, B, nullptr, 1234, nullptr, st, false);
   }
   g_prof = nullptr;
   g_launch_count = before;

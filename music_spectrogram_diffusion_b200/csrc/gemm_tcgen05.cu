@@ -11,11 +11,9 @@
 // Replaces the XLA dot_general lowering of DenseGeneral (msd/layers.py:397-442) for every
 // projection on the hot path.
 #include <stdlib.h>
-#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
-#include "sampler.cuh"
 
 namespace msd {
 
@@ -28,10 +26,6 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 __host__ __device__ inline bool epi_is_bf16_out(int e) {
   return e == EPI_BF16 || e == EPI_GATED_GELU || e == EPI_GATED_GELU_SPLIT3;
-}
-// epilogues that use the fp32 TMA store / reduce path (and its output tensor map)
-__host__ __device__ inline bool epi_is_f32_store(int e) {
-  return e == EPI_F32 || e == EPI_RESID_F32 || e == EPI_POS_F32;
 }
 
 // exact-tanh GELU of the fp32-accurate mode (flax.linen.gelu(approximate=True))
@@ -50,11 +44,6 @@ struct GemmDev {
   int pos_rows;
   const int* pos_shift;
   int dup_rows;
-  // CTA-pair kernel: A rows of a tile = tile_m * tile_row_step + rank * rank_row_stride
-  // (256 / 128 for an ordinary 256-row tile; EPI_SAMPLER: 128 / M/2, i.e. the two CTAs take the
-  // same frames of the conditional and the unconditional pass) over m_tiles tiles
-  int tile_row_step, rank_row_stride, m_tiles;
-  SamplerArgs samp;   // EPI_SAMPLER
 };
 
 template <int BN>
@@ -361,15 +350,13 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2] (leader's copy is the one used)
-  uint64_t* xfull_bar = tmem_empty_bar + 2;       // EPI_SAMPLER: odd CTA's accumulator is in its smem (even CTA's copy)
-  uint64_t* xfree_bar = xfull_bar + 1;            // EPI_SAMPLER: even CTA has read it (odd CTA's copy)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfree_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int num_kb = p.K / BLOCK_K;
-  const int m_pairs = p.m_tiles;
+  const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int n_tiles = p.N / BN;
   const int num_tiles = m_pairs * n_tiles;
   const int cluster_id = blockIdx.x >> 1;
@@ -387,11 +374,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
     }
-    mbar_init(xfull_bar, 1);
-    mbar_init(xfree_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2 && lane == 0 && epi_is_f32_store(p.epilogue)) tma_prefetch_desc(&tmap_out);
+  if (warp == 2 && lane == 0 && !epi_is_bf16_out(p.epilogue)) tma_prefetch_desc(&tmap_out);
   if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before_sync();
   cluster_sync_all();
@@ -415,7 +400,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       griddep_wait();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile % m_pairs) * p.tile_row_step + static_cast<int>(rank) * p.rank_row_stride;
+        const int m0 = (tile % m_pairs) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         const int n0 = (tile / m_pairs) * BN + static_cast<int>(rank) * Cfg::HALF_N;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -471,7 +456,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
       const int acc = tcount & 1;
       const uint32_t acc_ph = (tcount >> 1) & 1;
-      const int tile_row = (tile % m_pairs) * p.tile_row_step + static_cast<int>(rank) * p.rank_row_stride;
+      const int tile_row = (tile % m_pairs) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
       const int row0 = tile_row + lg * 32;
       const int n0 = (tile / m_pairs) * BN;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
@@ -496,54 +481,6 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                pack_bf16(v[6], v[7]));
           }
           epilogue_bf16_rows<4>(p, tile_smem, lane, row0, (n0 + c) / 2, ch);
-        }
-      } else if (p.epilogue == EPI_SAMPLER) {
-        // ---- final projection + reverse-diffusion update (diffusion_utils.py:398-453).  This
-        // CTA holds the model output of ONE pass for 128 frames x BN mel bins: the even CTA the
-        // conditional pass, the odd CTA the unconditional pass of the same frames.  The odd CTA
-        // parks its accumulator in its shared memory (swizzled rows, as the TMA-store path does)
-        // and arrives on the even CTA's barrier; the even CTA reads it through distributed shared
-        // memory and applies guidance, x0, clip, the DDPM / DDIM step and the noise to its rows.
-        const int trow = lg * 32 + lane;
-        const int frame = (tile % m_pairs) * p.tile_row_step + trow;   // row of z
-        const uint32_t xph = static_cast<uint32_t>(tcount) & 1u;
-        if (rank == 1) {
-          if (tcount > 0) mbar_wait_cluster(xfree_bar, (static_cast<uint32_t>(tcount) - 1u) & 1u);
-#pragma unroll 1
-          for (int c = 0; c < NCH; ++c) {
-            tmem_ld_32x32b_x32(t_row + c * 32, r);
-            tmem_ld_wait();
-            uint8_t* orow = sO + c * 16384 + trow * 128;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<uint4*>(orow + ((q ^ (trow & 7)) * 16)) =
-                  make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-          }
-          named_barrier_sync_c<1>(128);   // all 128 rows are parked
-          if (epi_leader) mbar_arrive_cluster(mapa_u32(xfull_bar, 0));
-        } else {
-          const SamplerArgs& sa = p.samp;
-          const int step = sa.run->step;      // stable: only the last CTA of this kernel advances it
-          const float* noise_base = sa.run->noise;
-          float* mel_base = sa.run->mel_out;
-          const unsigned long long seed = sa.run->seed;
-          mbar_wait_cluster(xfull_bar, xph);
-#pragma unroll 1
-          for (int c = 0; c < NCH; ++c) {
-            tmem_ld_32x32b_x32(t_row + c * 32, r);
-            tmem_ld_wait();
-            const uint32_t peer_row = mapa_u32(sO + c * 16384 + trow * 128, 1);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 mu = ld_cluster_f32x4(peer_row + ((q ^ (trow & 7)) * 16));
-              const float4 mo = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                            __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-              const long long idx = static_cast<long long>(frame) * sa.n_dims + n0 + c * 32 + q * 4;
-              sampler_update4(sa, step, noise_base, mel_base, seed, idx >> 2, mo, mu);
-            }
-          }
-          named_barrier_sync_c<1>(128);   // everyone is done with the peer's rows
-          if (epi_leader) mbar_arrive_cluster(mapa_u32(xfree_bar, 1));
         }
       } else if (p.epilogue == EPI_GATED_GELU_SPLIT3) {
         // fp32-accurate mode: exact tanh, result kept to ~16 mantissa bits as [hi | lo | hi]
@@ -657,22 +594,6 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
     }
   }
-  if (p.epilogue == EPI_SAMPLER && warp >= 2) {
-    // the step advance of the captured graph: every CTA has read the step (or never needed it) by
-    // the time it gets here; the last one to arrive decrements it for the next graph launch
-    const SamplerArgs& sa = p.samp;
-    const int step = sa.run->step;
-    prefetch_next_film(sa, step, static_cast<long long>(blockIdx.x) * 128 + (warp - 2) * 32 + lane);
-    named_barrier_sync_c<1>(128);
-    if (warp == 2 && lane == 0) {
-      __threadfence();
-      const unsigned int prev = atomicAdd(&sa.run->done, 1u);
-      if (prev == gridDim.x - 1) {
-        sa.run->done = 0u;
-        sa.run->step = step - 1;
-      }
-    }
-  }
   if (warp == 2 && lane == 0) tma_store_wait_all();
   tc_fence_before_sync();
   cluster_sync_all();
@@ -700,7 +621,8 @@ template <int BN>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                 const GemmDev& d, cudaStream_t st) {
   using Cfg = PairCfg<BN>;
-  const int num_tiles = d.m_tiles * (d.N / BN);
+  const int m_pairs = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_tiles = m_pairs * (d.N / BN);
   const int sms = gemm_sm_count();
   const int clusters = num_tiles < sms / 2 ? num_tiles : sms / 2;
   ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
@@ -801,10 +723,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   MSD_REQUIRE(pair || a.epilogue != EPI_GATED_GELU_SPLIT3,
               "gemm: the split-precision gated epilogue exists in the CTA-pair kernel only");
   MSD_REQUIRE(bn == 64 || bn == 128 || bn == 256 || (pair && bn == 192) ||
-                  (pair && bn == 96 && epi_is_f32_store(a.epilogue)),
+                  (pair && bn == 96 && !epi_is_bf16_out(a.epilogue)),
               "gemm: N=%d has no valid tile width (block_n %d)", a.N, bn);
   MSD_REQUIRE(a.N % bn == 0, "gemm: N=%d not a multiple of block_n=%d", a.N, bn);
-  MSD_REQUIRE(a.ldo % 8 == 0 || a.epilogue == EPI_SAMPLER, "gemm: ldo=%d must be a multiple of 8", a.ldo);
+  MSD_REQUIRE(a.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", a.ldo);
 
   CUtensorMap ta, tb;
   if (a.tmap_a) {
@@ -823,24 +745,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.out = a.out; d.ldo = a.ldo;
   d.resid = a.resid; d.pos = a.pos; d.pos_rows = a.pos_rows > 0 ? a.pos_rows : 1;
   d.pos_shift = a.pos_shift; d.dup_rows = a.dup_rows;
-  d.tile_row_step = 2 * BLOCK_M; d.rank_row_stride = BLOCK_M;
-  d.m_tiles = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  memset(&d.samp, 0, sizeof(d.samp));
-  if (a.epilogue == EPI_SAMPLER) {
-    MSD_REQUIRE(pair && a.sampler != nullptr && a.sampler->run != nullptr && a.sampler->passes == 2,
-                "gemm: the sampler epilogue needs the CTA-pair kernel, both guidance passes and "
-                "device-resident run arguments");
-    MSD_REQUIRE(a.M % (2 * BLOCK_M) == 0 && a.N == a.sampler->n_dims &&
-                    static_cast<long long>(a.M / 2) * a.N == a.sampler->n,
-                "gemm: sampler epilogue shape mismatch (M=%d N=%d n=%lld)", a.M, a.N, a.sampler->n);
-    d.samp = *a.sampler;
-    d.tile_row_step = BLOCK_M;        // 128 frames per tile ...
-    d.rank_row_stride = a.M / 2;      // ... of the conditional (even CTA) and unconditional pass
-    d.m_tiles = a.M / 2 / BLOCK_M;
-  }
   if (pair) {
     CUtensorMap tout = ta;  // placeholder unless the epilogue is an fp32 one
-    if (epi_is_f32_store(a.epilogue)) {
+    if (!epi_is_bf16_out(a.epilogue)) {
       const int rows = a.M + (a.epilogue == EPI_POS_F32 ? a.dup_rows : 0);
       if (int rc = make_tmap_f32_2d(&tout, a.out, rows, a.N, a.ldo, BLOCK_M)) return rc;
       // the residual epilogue adds into `out` with a TMA reduction: out must already hold resid

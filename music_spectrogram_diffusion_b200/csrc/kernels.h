@@ -82,20 +82,12 @@ enum GemmEpilogue : int {
   EPI_GATED_GELU = 3,  // out bf16 [M, N/2]: per 64 acc columns, gelu(acc[0:32]) * acc[32:64]
   EPI_POS_F32 = 4,     // out f32 = acc + pos[(r % pos_rows - shift[r / pos_rows]) mod pos_rows]
                        //   optionally duplicated to out[r + dup_rows]
-  EPI_SAMPLER = 6,     // final projection fused with the reverse-diffusion update (CTA-pair kernel):
-                       //   A rows [0, M/2) are the conditional pass, [M/2, M) the unconditional
-                       //   one; the pair's two CTAs take the SAME 128 frames of the two passes, the
-                       //   odd CTA hands its accumulator to the even one through distributed shared
-                       //   memory, which does guidance + x0 + clip + DDPM/DDIM update + noise +
-                       //   split-precision z for the next step (GemmArgs.sampler).  No `out`.
   EPI_GATED_GELU_SPLIT3 = 5,  // fp32-accurate mode: g = gelu(acc[0:32]) * acc[32:64] with the exact
                               //   tanh, written as bf16 [M, 3 * N/2] = [hi(g) | lo(g) | hi(g)]
                               //   (the A operand of a 3 x bf16 split-precision GEMM); CTA-pair kernel
 };
 
-struct SamplerArgs;
 struct GemmArgs {
-  const SamplerArgs* sampler;  // EPI_SAMPLER only (run must be set: device-resident step / arguments)
   const bf16* A;  // [M, lda]
   const bf16* B;  // [N, ldb]   (weights packed [out, in])
   int M, N, K;
