@@ -19,7 +19,6 @@ namespace msd {
 
 namespace {
 
-constexpr int PAIR_THREADS = 320;  // warps 0 TMA, 1 MMA, 2-5 epilogue team 0, 6-9 epilogue team 1
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
@@ -236,12 +235,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 //   warp 0 (one lane, both CTAs)   TMA producer (own A rows, own half of B), bytes credited to
 //                                  the leader's `full` barrier
 //   warp 1 (one lane, leader)      MMA issuer; commits multicast to both CTAs' barriers
-//   warps 2..9 (both CTAs)         epilogue of the CTA's own 128 accumulator rows: TWO teams of four
-//                                  warps (a warp reads the TMEM lanes 32 * (warp % 4) ..), team t
-//                                  takes the column chunks c = t (mod 2), each with its own staging
-//                                  slots, named barrier and TMA store groups -- the epilogue of the
-//                                  one-round kernels (the 768-wide projections) is exposed, two
-//                                  teams halve it
+//   warps 2..5 (both CTAs)         epilogue of the CTA's own 128 accumulator rows
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct PairCfg {
@@ -340,7 +334,7 @@ __device__ __forceinline__ void epilogue_bf16_rows(const GemmDev& p, uint8_t* ti
 }
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               const __grid_constant__ CUtensorMap tmap_b,
                               const __grid_constant__ CUtensorMap tmap_out, const GemmDev p) {
@@ -378,7 +372,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 16);  // 8 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -449,20 +443,15 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ---------------- epilogue: 2 teams x 4 warps, TMEM lane group = warp % 4 ----------------
+    // ---------------- epilogue: 4 warps, TMEM lane group = warp % 4 ----------------
     const int lg = warp & 3;
-    const int team = (warp - 2) >> 2;                       // 0: warps 2-5, 1: warps 6-9
-    uint8_t* tile_smem = sEpi + team * 32768 + lg * 4096;   // bf16 paths: per-warp transpose tile
-    uint8_t* sO = sEpi + team * 32768;                      // fp32 paths: this team's [2][16 KB] slots
+    uint8_t* tile_smem = sEpi + lg * 4096;
+    uint8_t* sO = sEpi;               // [4][16 KB]
     const bool has_res = p.epilogue == EPI_RESID_F32;
-    const bool epi_leader = ((warp == 2 || warp == 6) && lane == 0);
+    const bool epi_leader = (warp == 2 && lane == 0);
     constexpr int NCH = BN / 32;
-    uint32_t gc = 0;  // this team's running fp32 chunk counter (slot = gc & 1)
+    uint32_t gc = 0;  // running fp32 chunk counter (ring slot = gc & 3)
     int tcount = 0;
-    auto team_sync = [&]() {
-      if (team == 0) named_barrier_sync_c<1>(128);
-      else named_barrier_sync_c<2>(128);
-    };
     griddep_wait();  // residual reads / output writes come after the predecessor is complete
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
       const int acc = tcount & 1;
@@ -477,7 +466,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (p.epilogue == EPI_GATED_GELU) {
         uint32_t g[32];
 #pragma unroll 1
-        for (int c = team * 64; c < BN; c += 128) {
+        for (int c = 0; c < BN; c += 64) {
           tmem_ld_32x32b_x32(t_row + c, r);
           tmem_ld_32x32b_x32(t_row + c + 32, g);
           tmem_ld_wait();
@@ -498,7 +487,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t g[32];
         const int F = p.N / 2;
 #pragma unroll 1
-        for (int c = team * 64; c < BN; c += 128) {
+        for (int c = 0; c < BN; c += 64) {
           tmem_ld_32x32b_x32(t_row + c, r);
           tmem_ld_32x32b_x32(t_row + c + 32, g);
           tmem_ld_wait();
@@ -524,7 +513,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       } else if (p.epilogue == EPI_BF16) {
         uint32_t g[32];
 #pragma unroll 1
-        for (int c = team * 64; c < BN; c += 128) {
+        for (int c = 0; c < BN; c += 64) {
           tmem_ld_32x32b_x32(t_row + c, r);
           tmem_ld_32x32b_x32(t_row + c + 32, g);
           tmem_ld_wait();
@@ -548,14 +537,13 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // fp32 outputs: registers (+ position rows) -> swizzled smem tile -> one TMA store per
         // 128 x 32 chunk; the residual form (out == resid: x += acc, the only way the engine uses
         // it) is a TMA REDUCE-ADD straight into the residual stream, so the residual is never
-        // loaded: no load latency in the epilogue and half its memory traffic.  Two smem slots per
-        // team: the store of the team's chunk before last must have read its slot before the next
-        // chunk overwrites it.
+        // loaded: no load latency in the epilogue and half its memory traffic.  Four smem slots:
+        // the store of chunk c - 4 must have read its slot before chunk c overwrites it.
         const int trow = lg * 32 + lane;   // row inside the CTA's 128-row tile
         const int grow = tile_row + trow;  // global row
 #pragma unroll 1
-        for (int c = team; c < NCH; c += 2, ++gc) {
-          const uint32_t slot = gc & 1;
+        for (int c = 0; c < NCH; ++c, ++gc) {
+          const uint32_t slot = gc & 3;
           tmem_ld_32x32b_x32(t_row + c * 32, r);
           tmem_ld_wait();
           float v[32];
@@ -582,11 +570,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
             *reinterpret_cast<float4*>(orow + ((q ^ (trow & 7)) * 16)) =
                 make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           fence_proxy_async_smem();
-          // after this barrier the team may write its NEXT chunk's slot: its previous user is the
-          // store the leader issued one chunk ago (bulk groups are per thread: each team leader
-          // tracks its own), so nothing older than the newest group may still be reading
-          if (epi_leader) tma_store_wait_read<0>();
-          team_sync();
+          // after this barrier everyone may write the NEXT chunk's slot: its previous user is the
+          // store issued three chunks ago, so at most the two newest groups may still be reading
+          if (epi_leader) tma_store_wait_read<2>();
+          named_barrier_sync_c<1>(128);
           if (epi_leader) {
             if (tile_row < p.M) {  // M % 128 == 0: a CTA's rows are all valid or all padding
               if (has_res) {
@@ -607,7 +594,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
     }
   }
-  if ((warp == 2 || warp == 6) && lane == 0) tma_store_wait_all();
+  if (warp == 2 && lane == 0) tma_store_wait_all();
   tc_fence_before_sync();
   cluster_sync_all();
   if (warp == 1) {
@@ -641,7 +628,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
                  2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
                      4.0 * d.M * d.N, st);
-  MSD_CUDA_CHECK(launch_kernel(gemm_bf16_tcgen05_pair_kernel<BN>, dim3(2 * clusters), dim3(PAIR_THREADS),
+  MSD_CUDA_CHECK(launch_kernel(gemm_bf16_tcgen05_pair_kernel<BN>, dim3(2 * clusters), dim3(192),
                                Cfg::SMEM_BYTES, st, ta, tb, tout, d));
   ++g_launch_count;
   return 0;
