@@ -1394,6 +1394,41 @@ int msd_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t va
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   *ms_out = ms / iters;
+  if (getenv("MSD_GEMM_TRACE") && variant != 1 && rc == 0 && e == cudaSuccess) {
+    // one more launch with per-CTA stamps (after a warm one right before it, like in the loop)
+    long long* tr = nullptr;
+    if (tb.get(&tr, 8 * 512) == 0) {
+      cudaMemsetAsync(tr, 0, 8 * 512 * sizeof(long long), st);
+      launch_gemm(ga, st);
+      ga.trace = tr;
+      launch_gemm(ga, st);
+      ga.trace = nullptr;
+      std::vector<long long> h(8 * 512);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h.data(), tr, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long t0 = 0, t1 = 0;
+      int n = 0;
+      double sum[5] = {0, 0, 0, 0, 0};
+      for (int b = 0; b < 512; ++b) {
+        const long long* r = &h[b * 8];
+        if (r[1] == 0) continue;
+        if (n == 0 || r[1] < t0) t0 = r[1];
+        if (n == 0 || r[2] > t1) t1 = r[2];
+        // r[3] = total cycles; r[4..7] absolute clock64 stamps; entry clock = exit - total
+        sum[0] += static_cast<double>(r[3]);
+        ++n;
+      }
+      fprintf(stderr, "[gemm trace] M=%d N=%d K=%d epi=%d: %d CTAs, first entry -> last exit %.2f us, mean "
+              "cycles in CTA %.0f\n", M, N, K, epilogue, n, (t1 - t0) * 1e-3, n ? sum[0] / n : 0.0);
+      for (int b = 0; b < 4 && b < 512; ++b) {
+        const long long* r = &h[b * 8];
+        if (r[1] == 0) continue;
+        fprintf(stderr, "[gemm trace]   CTA %d sm %lld: entry +%.2f us, exit +%.2f us; cycles: total %lld, "
+                "setup->wait %lld, wait->acc %lld, acc->stored %lld\n", b, r[0], (r[1] - t0) * 1e-3,
+                (r[2] - t0) * 1e-3, r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6]);
+      }
+    }
+  }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaStreamDestroy(st);

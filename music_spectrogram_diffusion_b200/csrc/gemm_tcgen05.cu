@@ -44,6 +44,10 @@ struct GemmDev {
   int pos_rows;
   const int* pos_shift;
   int dup_rows;
+  // debugging (MSD_GEMM_TRACE with msd_bench_gemm): per CTA 8 int64 -- smid, globaltimer at entry /
+  // exit, then clock64 at: entry, set-up done (after the cluster sync), dependency wait returned
+  // (epilogue warp), first accumulator ready, last chunk stored, exit
+  long long* trace;
 };
 
 template <int BN>
@@ -355,6 +359,14 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  long long* trc = (p.trace != nullptr && threadIdx.x == 64) ? p.trace + blockIdx.x * 8 : nullptr;
+  if (trc) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trc[0] = smid; trc[1] = t; trc[3] = clock64();
+  }
   const int num_kb = p.K / BLOCK_K;
   const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int n_tiles = p.N / BN;
@@ -382,6 +394,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (trc) trc[4] = clock64();
 
   griddep_launch_dependents();
   if (warp == 0) {
@@ -453,6 +466,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t gc = 0;  // running fp32 chunk counter (ring slot = gc & 3)
     int tcount = 0;
     griddep_wait();  // residual reads / output writes come after the predecessor is complete
+    if (trc) trc[5] = clock64();
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
       const int acc = tcount & 1;
       const uint32_t acc_ph = (tcount >> 1) & 1;
@@ -461,6 +475,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n0 = (tile / m_pairs) * BN;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
+      if (trc && tcount == 0) trc[6] = clock64();
       const uint32_t t_row = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
       uint32_t r[32];
       if (p.epilogue == EPI_GATED_GELU) {
@@ -594,9 +609,16 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
     }
   }
+  if (trc) trc[7] = clock64();
   if (warp == 2 && lane == 0) tma_store_wait_all();
   tc_fence_before_sync();
   cluster_sync_all();
+  if (trc) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trc[2] = t;
+    trc[3] = clock64() - trc[3];   // total cycles in the CTA; the stamps below become offsets
+  }
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
@@ -745,6 +767,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.out = a.out; d.ldo = a.ldo;
   d.resid = a.resid; d.pos = a.pos; d.pos_rows = a.pos_rows > 0 ? a.pos_rows : 1;
   d.pos_shift = a.pos_shift; d.dup_rows = a.dup_rows;
+  d.trace = a.trace;
   if (pair) {
     CUtensorMap tout = ta;  // placeholder unless the epilogue is an fp32 one
     if (!epi_is_bf16_out(a.epilogue)) {

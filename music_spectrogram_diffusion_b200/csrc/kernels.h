@@ -105,6 +105,7 @@ struct GemmArgs {
   const CUtensorMap* tmap_b;
   int block_n;           // 0 = auto
   int variant;           // 0 = CTA-pair persistent kernel (default), 1 = single-CTA kernel
+  long long* trace;      // debugging: per-CTA stamps of the CTA-pair kernel (8 int64 per CTA), or null
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 int gemm_configure();  // opt in to the kernels' dynamic shared memory sizes (idempotent)
