@@ -610,10 +610,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   }
   if (trc) trc[7] = clock64();
-  // the staging slots must have been read before the CTA's shared memory goes away; the writes
-  // themselves are complete and visible when the grid completes (what the dependent kernel's
-  // griddepcontrol.wait / the next stream operation waits for), so nothing waits for them here
-  if (warp == 2 && lane == 0) tma_store_wait_read<0>();
+  if (warp == 2 && lane == 0) tma_store_wait_all();
   tc_fence_before_sync();
   cluster_sync_all();
   if (trc) {
