@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MSD_B200_ABI_VERSION 3
+#define MSD_B200_ABI_VERSION 4
 
 typedef struct msd_ctx msd_ctx;
 
@@ -215,6 +215,23 @@ int msd_op_dense_epilogue(const float* a, const float* w, const float* w1, int32
                           int32_t K, int32_t epilogue, int32_t block_n, const float* resid,
                           const float* pos, int32_t pos_rows, const int32_t* pos_shift,
                           int32_t dup_rows, float* out, void* stream);
+
+/* The deferred-normalisation pair of the bf16 hot path: a residual projection
+ * whose epilogue also prepares the next pre-norm, and the projection that consumes it.
+ *   stage 1   x_out [M, d] = x + a w_out;  operand = bf16(x_out * g(row)), g = g_lo for rows <
+ *             split_row, else g_hi;  row sums of squares of x_out kept per column tile
+ *   stage 2   y [M, N2] = bf16(rsqrt(mean(x_out^2) + 1e-6)[row] * (operand w2) + bias)     (w2b NULL)
+ *             y = bf16(gelu_tanh(u) * u1), u | u1 the same through w2 | w2b                (gated)
+ * i.e. y == bf16((rmsnorm(x_out) * g) w2 + bias) up to operand rounding (layers.py:632-666 with
+ * g = scale * (1 + film_scale), bias = film_bias w2).  a [M, K], w_out [K, d], x [M, d], g_* [d],
+ * w2 / w2b [d, N2], bias [N2] (gated: [2 * N2] in accumulator column order: 32 of w2, 32 of w2b,
+ * ...) or NULL; all f32 device, a / w_out / w2 / w2b bf16-rounded by the callee.  block_n1 /
+ * block_n2: tile widths of the two GEMMs (0 = auto).  Outputs f32 device. */
+int msd_op_dense_deferred_norm(const float* a, const float* w_out, const float* x, int32_t M, int32_t d,
+                               int32_t K, const float* g_lo, const float* g_hi, int32_t split_row,
+                               const float* w2, const float* w2b, int32_t N2, const float* bias,
+                               int32_t block_n1, int32_t block_n2, float* x_out, float* y_out,
+                               void* stream);
 
 /* dot_product_attention of the fp32-accurate mode: as msd_op_attention, but q / k / v are used in
  * full fp32 and the result is returned as hi + lo of the kernel's [hi | lo | hi] output. */

@@ -134,9 +134,11 @@ SYMBOLS = [
     ('msd_op_jax_normal', ctypes.c_int, [ctypes.c_uint64, _I, ctypes.c_int64, _P, _P]),
     ('msd_op_jax_bits', ctypes.c_int, [ctypes.c_uint64, _I, ctypes.c_int64, _P, _P]),
     ('msd_op_dense_epilogue', ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P]),
+    ('msd_op_dense_deferred_norm', ctypes.c_int,
+     [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
     ('msd_op_attention_f32', ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
 ]
-ABI_VERSION = 3  # MSD_B200_ABI_VERSION of include/msd_b200.h this binding was written against
+ABI_VERSION = 4  # MSD_B200_ABI_VERSION of include/msd_b200.h this binding was written against
 
 _lib: Optional[ctypes.CDLL] = None
 

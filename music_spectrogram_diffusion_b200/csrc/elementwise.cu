@@ -42,6 +42,10 @@ struct NormDev {
   long long film_step_stride, film_offset;
   int rows, d, ldo, split3;
   int src_len, dst_len, dst_off;  // row remap when src_len > 0
+  // deferred normalisation (launch_prep_rows): out = bf16(x * gamma) with gamma taken at
+  // gamma + (*step) * gamma_step_stride, NOT normalised; ss_out[row] = sum of squares
+  float* ss_out;
+  long long gamma_step_stride;
 };
 
 constexpr int NORM_MAX_ITERS = 8;  // d <= 1024
@@ -59,9 +63,11 @@ __global__ void __launch_bounds__(256) rmsnorm_film_kernel(const NormDev p) {
   constexpr int D = ITERS * 128;
   // per-segment constants: safe to read ahead of the dependency wait (written at load time)
   float4 g[ITERS];
+  // (the step index only changes in the last kernel of a step: stable from here on)
+  const float* gamma = p.ss_out ? p.gamma + static_cast<long long>(*p.step) * p.gamma_step_stride : p.gamma;
 #pragma unroll
   for (int i = 0; i < ITERS; ++i)
-    g[i] = __ldg(reinterpret_cast<const float4*>(p.gamma + (i * 32 + lane) * 4));
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
   griddep_wait();
   const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(warp) * D);
   float4 v[ITERS];
@@ -84,7 +90,8 @@ __global__ void __launch_bounds__(256) rmsnorm_film_kernel(const NormDev p) {
   for (int i = 0; i < ITERS; ++i)
     ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   ss = warp_sum(ss);
-  const float inv = rsqrtf(ss / static_cast<float>(D) + 1e-6f);
+  const float inv = p.ss_out ? 1.0f : rsqrtf(ss / static_cast<float>(D) + 1e-6f);
+  if (p.ss_out && lane == 0) p.ss_out[warp] = ss;
   int orow = warp;
   if (p.src_len > 0) {
     const int b = warp / p.src_len;
@@ -358,11 +365,18 @@ __device__ __forceinline__ void sampler_step_body(const SamplerArgs& a, int step
 }
 
 __device__ __forceinline__ void prefetch_next_film(const SamplerArgs& a, int step, long long gid) {
-  if (a.film == nullptr || step < 1) return;
-  const long long off = gid * 32;  // one 128-byte line per thread
-  if (off < a.film_step_floats) {
+  if (step < 1) return;
+  const long long off = gid * 32;  // one 128-byte line per thread and table
+  if (a.film != nullptr && off < a.film_step_floats) {
     const float* ptr = a.film + static_cast<long long>(step - 1) * a.film_step_floats + off;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (a.pf[t] != nullptr && off < a.pf_step_floats[t]) {
+      const float* ptr = a.pf[t] + static_cast<long long>(step - 1) * a.pf_step_floats[t] + off;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
   }
 }
 
@@ -658,7 +672,24 @@ int launch_rmsnorm(const float* x, const float* gamma, int rows, int d, bf16* ou
   p.film_step_stride = film_step_stride; p.film_offset = film_offset;
   p.rows = rows; p.d = d; p.ldo = ldo; p.split3 = split3;
   p.src_len = 0; p.dst_len = 0; p.dst_off = 0;
+  p.ss_out = nullptr; p.gamma_step_stride = 0;
   ProfScope prof(KC_NORM, 0.0, static_cast<double>(rows) * d * (4.0 + (split3 ? 6.0 : 2.0)), stream);
+  MSD_TRY_RC(launch_norm(p, stream));
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_prep_rows(const float* x, const float* g, long long g_step_stride, const int* step, int rows,
+                     int d, bf16* a_out, int lda, float* ss_out, cudaStream_t stream) {
+  MSD_REQUIRE(d % 128 == 0 && d <= 128 * NORM_MAX_ITERS, "prep_rows: d=%d must be k*128 <= 1024", d);
+  MSD_REQUIRE(x && g && step && a_out && ss_out, "prep_rows: null argument");
+  NormDev p;
+  p.x = x; p.gamma = g; p.out = a_out; p.film = nullptr; p.step = step;
+  p.film_step_stride = 0; p.film_offset = 0;
+  p.rows = rows; p.d = d; p.ldo = lda; p.split3 = 0;
+  p.src_len = 0; p.dst_len = 0; p.dst_off = 0;
+  p.ss_out = ss_out; p.gamma_step_stride = g_step_stride;
+  ProfScope prof(KC_NORM, 0.0, static_cast<double>(rows) * d * 6.0, stream);
   MSD_TRY_RC(launch_norm(p, stream));
   ++g_launch_count;
   return 0;
@@ -673,6 +704,7 @@ int launch_rmsnorm_rows_remap(const float* x, const float* gamma, int B, int src
   p.film_step_stride = 0; p.film_offset = 0;
   p.rows = B * src_len; p.d = d; p.ldo = split3 ? 3 * d : d; p.split3 = split3;
   p.src_len = src_len; p.dst_len = dst_len; p.dst_off = dst_off;
+  p.ss_out = nullptr; p.gamma_step_stride = 0;
   MSD_TRY_RC(launch_norm(p, stream));
   ++g_launch_count;
   return 0;
@@ -805,6 +837,68 @@ int launch_mask_bits(const int* mask, int nb, int L, uint32_t* bits, cudaStream_
   MSD_REQUIRE(L % 128 == 0, "mask_bits: L must be a multiple of 128");
   const long long words = static_cast<long long>(nb) * (L / 32);
   mask_bits_kernel<<<blocks_for(words * 32, 256), 256, 0, stream>>>(mask, words, bits);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Deferred-normalisation tables (load time).  gain[s, :] = gamma * (1 + film_scale[s, :]);
+// bias[s, n] = sum_k film_bias[s, k] * W[n, k] (W: packed bf16 weight rows, as the GEMM reads them).
+__global__ void film_gain_kernel(const float* __restrict__ film, long long film_stride,
+                                 const float* __restrict__ gamma, float* __restrict__ out,
+                                 long long out_stride, int steps, int d) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(steps) * d) return;
+  const int s = static_cast<int>(i / d), k = static_cast<int>(i - static_cast<long long>(s) * d);
+  out[s * out_stride + k] = gamma[k] * (1.0f + film[s * film_stride + k]);
+}
+constexpr int FB_STEPS = 8;
+__global__ void __launch_bounds__(128)
+film_bias_kernel(const float* __restrict__ fb, long long fb_stride, const bf16* __restrict__ W,
+                 int ldw, float* __restrict__ out, long long out_stride, int steps, int N, int K) {
+  extern __shared__ float s_fb[];  // [FB_STEPS][K]
+  const int s0 = blockIdx.y * FB_STEPS;
+  for (int i = threadIdx.x; i < FB_STEPS * K; i += blockDim.x) {
+    const int s = i / K, k = i - s * K;
+    s_fb[i] = (s0 + s < steps) ? fb[(s0 + s) * fb_stride + k] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc[FB_STEPS];
+#pragma unroll
+  for (int s = 0; s < FB_STEPS; ++s) acc[s] = 0.f;
+  const uint4* wr = reinterpret_cast<const uint4*>(W + static_cast<size_t>(n) * ldw);
+  for (int k8 = 0; k8 < K / 8; ++k8) {
+    const uint4 u = wr[k8];
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float w0 = __uint_as_float(uu[j] << 16), w1 = __uint_as_float(uu[j] & 0xffff0000u);
+#pragma unroll
+      for (int s = 0; s < FB_STEPS; ++s) {
+        acc[s] = fmaf(s_fb[s * K + k8 * 8 + 2 * j], w0, acc[s]);
+        acc[s] = fmaf(s_fb[s * K + k8 * 8 + 2 * j + 1], w1, acc[s]);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < FB_STEPS; ++s)
+    if (s0 + s < steps) out[(s0 + s) * out_stride + n] = acc[s];
+}
+int launch_film_gain(const float* film, long long film_stride, const float* gamma, float* out,
+                     long long out_stride, int steps, int d, cudaStream_t stream) {
+  film_gain_kernel<<<blocks_for(static_cast<long long>(steps) * d, 256), 256, 0, stream>>>(
+      film, film_stride, gamma, out, out_stride, steps, d);
+  MSD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_film_bias(const float* fb, long long fb_stride, const bf16* W, int ldw, float* out,
+                     long long out_stride, int steps, int N, int K, cudaStream_t stream) {
+  MSD_REQUIRE(K % 8 == 0 && ldw % 8 == 0 && FB_STEPS * K * 4 <= 48 * 1024,
+              "film_bias: K=%d must be a multiple of 8 and <= 1536", K);
+  dim3 grid((N + 127) / 128, (steps + FB_STEPS - 1) / FB_STEPS);
+  film_bias_kernel<<<grid, 128, FB_STEPS * K * sizeof(float), stream>>>(fb, fb_stride, W, ldw, out,
+                                                                       out_stride, steps, N, K);
   MSD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -74,7 +74,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 
 static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-                        uint64_t ld, uint32_t box_rows, int elem_bytes);
+                        uint64_t ld, uint32_t box_rows, int elem_bytes, int inner_bytes = 128);
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows) {
@@ -84,9 +84,13 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
                      uint64_t ld, uint32_t box_rows) {
   return make_tmap_2d(out, base, rows, cols, ld, box_rows, 4);
 }
+int make_tmap_bf16_2d_half(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(out, base, rows, cols, ld, box_rows, 2, 64);
+}
 
 static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-                        uint64_t ld, uint32_t box_rows, int elem_bytes) {
+                        uint64_t ld, uint32_t box_rows, int elem_bytes, int inner_bytes) {
   if (g_encode == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -100,13 +104,14 @@ static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
   MSD_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u out of range", box_rows);
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * elem_bytes};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(inner_bytes / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                              : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                         2, const_cast<void*>(base), gdim,
                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MSD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%llu cols=%llu ld=%llu)",
               (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
@@ -174,6 +179,9 @@ struct Encoder {
 
 using namespace msd;
 
+// most column tiles a residual projection can have (narrowest CTA-pair tile: 64 columns of d <= 1024)
+static constexpr size_t kSsParts = 16;
+
 struct msd_ctx {
   msd_config cfg;
   int device = 0;
@@ -220,6 +228,15 @@ struct msd_ctx {
   float* attn_part_o2 = nullptr;  // second scratch set: sum_cross_attends launches two cross-
   float* attn_part_ml2 = nullptr; //   attentions back to back (PDL lets them overlap)
   uint32_t* attn_flags2 = nullptr;
+  // deferred normalisation (bf16 mode; kernels.h GemmPrep / GemmRowScale): no stand-alone rmsnorm
+  // kernels inside the decoder layers
+  bool fused_norm = false;
+  float* gtab = nullptr;      // [steps, 2*Ld, d]  gamma * (1 + FiLM scale): j = 2l self, 2l+1 mlp
+  float* btab_qkv = nullptr;  // [steps, Ld, 3*hh] FiLM bias row through the QKV weights
+  float* btab_wi = nullptr;   // [steps, Ld, 2*F]  FiLM bias row through the packed wi weights
+  float* ss_x = nullptr;      // partial row sums of squares [kSsParts, R]: stream entering a layer
+  float* ss_so = nullptr;     //   ... after the self-attention projection
+  float* ss_co = nullptr;     //   ... after the cross-attention projection
   float* eps = nullptr;    // [R, nd]
   float* z = nullptr;      // [B*N*nd]
   bf16* z_split = nullptr; // [B*N, 3*nd]
@@ -608,6 +625,32 @@ static int load_all(msd_ctx* c, Loader& L) {
         if (cudaStreamSynchronize(L.st) != cudaSuccess) { rc = -2; break; }
       }
     }
+    if (rc != 0 || !c->fused_norm) break;
+    // deferred normalisation: per step and layer, the column gains and the FiLM bias rows pushed
+    // through the QKV / wi weights (as the GEMM reads them: packed bf16)
+    const int hh = c->hh, F = c->F;
+    const long long fstride = static_cast<long long>(2) * Ld * 2 * d;
+    if ((rc = A.alloc(&c->gtab, static_cast<size_t>(steps) * 2 * Ld * d))) break;
+    if ((rc = A.alloc(&c->btab_qkv, static_cast<size_t>(steps) * Ld * 3 * hh))) break;
+    if ((rc = A.alloc(&c->btab_wi, static_cast<size_t>(steps) * Ld * 2 * F))) break;
+    for (int l = 0; l < Ld && rc == 0; ++l) {
+      const DecLayer& w = c->dec[l];
+      for (int f = 0; f < 2 && rc == 0; ++f) {
+        const float* film = c->film + static_cast<size_t>(2 * l + f) * 2 * d;
+        rc = launch_film_gain(film, fstride, f == 0 ? w.ln_self : w.ln_mlp,
+                              c->gtab + static_cast<size_t>(2 * l + f) * d,
+                              static_cast<long long>(2) * Ld * d, steps, d, L.st);
+      }
+      if (rc == 0)
+        rc = launch_film_bias(c->film + static_cast<size_t>(2 * l) * 2 * d + d, fstride, w.self_attn.qkv,
+                              d, c->btab_qkv + static_cast<size_t>(l) * 3 * hh,
+                              static_cast<long long>(Ld) * 3 * hh, steps, 3 * hh, d, L.st);
+      if (rc == 0)
+        rc = launch_film_bias(c->film + static_cast<size_t>(2 * l + 1) * 2 * d + d, fstride, w.mlp.wi, d,
+                              c->btab_wi + static_cast<size_t>(l) * 2 * F,
+                              static_cast<long long>(Ld) * 2 * F, steps, 2 * F, d, L.st);
+    }
+    if (rc == 0 && cudaStreamSynchronize(L.st) != cudaSuccess) rc = -2;
   } while (0);
   cudaFree(d_timing);
   cudaFree(c1);
@@ -795,6 +838,120 @@ static int decoder_layers(msd_ctx* c, int seg0, int nseg, int ncross, cudaStream
   return 0;
 }
 
+// The same 12 DecoderLayers with DEFERRED NORMALISATION (bf16 mode, one chain; kernels.h GemmPrep /
+// GemmRowScale): every pre-norm (+FiLM) of layers.py:632-666 is split into a column gain applied
+// where the residual stream is produced and a row scale + bias row applied where the next
+// projection's accumulator is drained,
+//     (rmsnorm(x) gamma (1 + fs) + fb) W  ==  rsqrt(mean(x^2) + eps) * ((x gamma (1 + fs)) W) + fb W,
+// so no stand-alone rmsnorm kernel runs inside the layers (35 fewer kernels per step).
+//   xn      bf16 operand of the next projection: x * g' (unnormalised)
+//   ss_x    row sums of squares of x entering a layer (prep kernel, then each wo projection)
+//   ss_so   ... after the self-attention output projection; ss_co after the cross-attention one
+// Rows of the unconditional pass (>= ncross * N) skip the cross-attention block: their operand for
+// the MLP is written by the self-attention projection already (g_hi), their row sums stay in ss_so.
+static int decoder_layers_fused(msd_ctx* c, int nseg, int ncross, cudaStream_t st) {
+  const int d = c->d, hh = c->hh, F = c->F, N = c->N;
+  const int R = nseg * N, Rc = ncross * N;
+  const int Ld = c->cfg.num_decoder_layers;
+  const int nsrc = c->cfg.cross_attend_style == 1 ? 2 : 1;
+  const long long gstride = static_cast<long long>(2) * Ld * d;
+  const int ss_stride = c->passes * c->Bmax * N;
+  float* x = c->x;
+  bf16* xn = c->xn;
+  auto base_args = [&](const bf16* A, int lda, const bf16* W, int M, int Nn, int K, int epi, void* out,
+                       int ldo) {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.B = W; a.M = M; a.N = Nn; a.K = K; a.lda = lda; a.ldb = K;
+    a.epilogue = epi; a.out = out; a.ldo = ldo; a.step = c->d_step;
+    return a;
+  };
+  // residual projection + operand / row sums for what follows
+  auto resid_prep = [&](const bf16* A, const bf16* W, int M, int K, const float* g_lo, long long s_lo,
+                        const float* g_hi, long long s_hi, int split_row, float* ss, int* parts) {
+    GemmArgs a = base_args(A, K, W, M, d, K, EPI_RESID_PREP, x, d);
+    a.resid = x;
+    a.prep.g_lo = g_lo; a.prep.g_lo_step_stride = s_lo;
+    a.prep.g_hi = g_hi; a.prep.g_hi_step_stride = s_hi;
+    a.prep.split_row = split_row;
+    a.prep.a = xn; a.prep.lda = d;
+    a.prep.ss = ss; a.prep.ss_stride = ss_stride;
+    *parts = d / gemm_pick_pair_bn(M, d);
+    return launch_gemm(a, st);
+  };
+  auto row_scale = [&](GemmArgs& a, const float* lo, int parts_lo, const float* hi, int parts_hi,
+                       int split_row, const float* bias, long long bias_stride) {
+    a.rs.ss_lo = lo; a.rs.parts_lo = parts_lo; a.rs.ss_hi = hi; a.rs.parts_hi = parts_hi;
+    a.rs.split_row = split_row; a.rs.ss_stride = ss_stride; a.rs.inv_d = 1.0f / static_cast<float>(d);
+    a.rs.col_bias = bias; a.rs.bias_step_stride = bias_stride;
+  };
+  // layer 0: the stream comes from the input projection, not from a residual epilogue
+  MSD_TRY(launch_prep_rows(x, c->gtab, gstride, c->d_step, R, d, xn, d, c->ss_x, st));
+  int parts_x = 1, parts_so = 1, parts_co = 1;
+  for (int l = 0; l < Ld; ++l) {
+    const DecLayer& w = c->dec[l];
+    const float* g_mlp = c->gtab + static_cast<size_t>(2 * l + 1) * d;
+    // self-attention block (174-193)
+    {
+      GemmArgs a = base_args(xn, d, w.self_attn.qkv, R, 3 * hh, d, EPI_BF16, c->qkv, 3 * hh);
+      row_scale(a, c->ss_x, parts_x, c->ss_x, parts_x, R, c->btab_qkv + static_cast<size_t>(l) * 3 * hh,
+                static_cast<long long>(Ld) * 3 * hh);
+      MSD_TRY(launch_gemm(a, st));
+    }
+    MSD_TRY(attention(c, c->qkv, 0, 3 * hh, c->qkv, hh, 3 * hh, c->qkv, 2 * hh, 3 * hh, c->attn, hh, 0,
+                      nseg, c->H, N, N, nullptr, 0, st));
+    // x += attn W_out; rows that cross-attend get the cross pre-norm's gain, the others the MLP's
+    MSD_TRY(resid_prep(c->attn, w.self_attn.out, R, hh, Rc > 0 ? w.ln_cross : g_mlp, Rc > 0 ? 0 : gstride,
+                       g_mlp, gstride, Rc, c->ss_so, &parts_so));
+    // cross-attention block (196-235), conditioned rows only
+    if (Rc > 0) {
+      GemmArgs a = base_args(xn, d, w.cross_q, Rc, nsrc * hh, d, EPI_BF16, c->qc, nsrc * hh);
+      row_scale(a, c->ss_so, parts_so, c->ss_so, parts_so, Rc, nullptr, 0);
+      MSD_TRY(launch_gemm(a, st));
+      const size_t kv_off = static_cast<size_t>(l) * c->Bmax * c->Mkv * 2 * hh;
+      AttnExtra ex;
+      ex.part_o = c->attn_part_o; ex.part_ml = c->attn_part_ml; ex.flags = c->attn_flags;
+      ex.kv_static = 1;
+      if (nsrc == 1) {
+        MSD_TRY(attention(c, c->qc, 0, hh, c->kv_cache, kv_off, 2 * hh, c->kv_cache, kv_off + hh, 2 * hh,
+                          c->attn, hh, 0, ncross, c->H, N, c->Mkv, c->mask_bits, c->Mkv / 32, st, ex));
+        MSD_TRY(resid_prep(c->attn, w.cross_out, Rc, hh, g_mlp, gstride, g_mlp, gstride, Rc, c->ss_co,
+                           &parts_co));
+      } else {
+        ex.kv_batch_rows = c->Mkv;
+        ex.kv_row0 = 0;
+        MSD_TRY(attention(c, c->qc, 0, 2 * hh, c->kv_cache, kv_off, 2 * hh, c->kv_cache, kv_off + hh,
+                          2 * hh, c->attn2, 2 * hh, 0, ncross, c->H, N, c->T, c->mask_bits, c->Mkv / 32,
+                          st, ex));
+        ex.kv_row0 = c->T;
+        ex.part_o = c->attn_part_o2; ex.part_ml = c->attn_part_ml2; ex.flags = c->attn_flags2;
+        MSD_TRY(attention(c, c->qc, hh, 2 * hh, c->kv_cache, kv_off, 2 * hh, c->kv_cache, kv_off + hh,
+                          2 * hh, c->attn2, 2 * hh, hh, ncross, c->H, N, c->C, c->mask_bits + c->T / 32,
+                          c->Mkv / 32, st, ex));
+        MSD_TRY(resid_prep(c->attn2, w.cross_out, Rc, 2 * hh, g_mlp, gstride, g_mlp, gstride, Rc,
+                           c->ss_co, &parts_co));
+      }
+    }
+    // MLP block (241-256)
+    {
+      GemmArgs a = base_args(xn, d, w.mlp.wi, R, 2 * F, d, EPI_GATED_GELU, c->hmid, F);
+      if (Rc > 0) row_scale(a, c->ss_co, parts_co, c->ss_so, parts_so, Rc,
+                            c->btab_wi + static_cast<size_t>(l) * 2 * F, static_cast<long long>(Ld) * 2 * F);
+      else row_scale(a, c->ss_so, parts_so, c->ss_so, parts_so, R,
+                     c->btab_wi + static_cast<size_t>(l) * 2 * F, static_cast<long long>(Ld) * 2 * F);
+      MSD_TRY(launch_gemm(a, st));
+    }
+    if (l + 1 < Ld) {
+      const float* g_next = c->gtab + static_cast<size_t>(2 * (l + 1)) * d;
+      MSD_TRY(resid_prep(c->hmid, w.mlp.wo, R, F, g_next, gstride, g_next, gstride, R, c->ss_x, &parts_x));
+    } else {
+      // the decoder_norm that follows is a stand-alone (split-precision) kernel reading x itself
+      MSD_TRY(dense(c, c->hmid, w.mlp.wo, R, d, F, EPI_RESID_F32, x, d, x, st));
+    }
+  }
+  return 0;
+}
+
 // Decoder.__call__ (network.py:360-457) over `total` segments of which the first `ncond`
 // cross-attend to the cached encodings.  Input: c->z_split; output: c->eps [total*N, nd].
 // With `two_streams` the conditional and unconditional passes -- independent until the guidance
@@ -823,7 +980,8 @@ static int run_decoder(msd_ctx* c, int B, int ncond, int total, cudaStream_t st,
     g_pdl_skip_next = true;  // the join kernel has two predecessors
   } else {
     // one chain, both passes batched per kernel except the cross-attention block
-    MSD_TRY(decoder_layers(c, 0, total, ncond, st));
+    if (c->fused_norm) MSD_TRY(decoder_layers_fused(c, total, ncond, st));
+    else MSD_TRY(decoder_layers(c, 0, total, ncond, st));
   }
   // decoder_norm + spec_out_dense in split precision (445-456: fp32 "for stability")
   MSD_TRY(launch_rmsnorm(c->x, c->dec_norm, R, d, c->xn, 3 * d, nullptr, nullptr, 0, 0, 1, st));
@@ -846,6 +1004,14 @@ static int sampler_step(msd_ctx* c, int B, const float* noise, unsigned long lon
   a.run = use_run ? c->run : nullptr;
   a.film = c->film;
   a.film_step_floats = static_cast<long long>(2) * c->cfg.num_decoder_layers * 2 * c->d;
+  if (c->fused_norm) {
+    // the layers read the derived tables instead of the FiLM rows
+    const long long Ld = c->cfg.num_decoder_layers;
+    a.film = nullptr;
+    a.pf[0] = c->gtab; a.pf_step_floats[0] = 2 * Ld * c->d;
+    a.pf[1] = c->btab_qkv; a.pf_step_floats[1] = Ld * 3 * c->hh;
+    a.pf[2] = c->btab_wi; a.pf_step_floats[2] = Ld * 2 * c->F;
+  }
   if (use_run && c->xrole != 0) {
     a.passes = 2;   // both passes exist, one of them on the peer GPU
     a.xrole = c->xrole; a.xlocal = c->xchg; a.xpeer = c->xchg_peer;
@@ -991,6 +1157,16 @@ int msd_create(const msd_config* cfg, int device, msd_ctx** out) {
         set_error("msd_create: cudaMemset failed");
         rc = -2;
         break;
+      }
+    }
+    {
+      // MSD_FUSED_NORM=0: tuning / test hook, keeps the stand-alone rmsnorm kernels
+      const char* fn = getenv("MSD_FUSED_NORM");
+      c->fused_norm = !c->acc && !c->two_streams && !(fn && fn[0] == '0');
+      if (c->fused_norm) {
+        if ((rc = A.alloc(&c->ss_x, kSsParts * R))) break;
+        if ((rc = A.alloc(&c->ss_so, kSsParts * R))) break;
+        if ((rc = A.alloc(&c->ss_co, kSsParts * R))) break;
       }
     }
     if ((rc = A.alloc(&c->eps, R * c->nd))) break;
@@ -1622,6 +1798,59 @@ int msd_op_dense_epilogue(const float* a, const float* w, const float* w1, int32
   MSD_TRY(launch_gemm(ga, st));
   if (bf16_out)
     MSD_TRY(launch_bf16_rows_to_f32(ob, N * ks, split ? N : 0, out, M, N, st));
+  MSD_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int msd_op_dense_deferred_norm(const float* a, const float* w_out, const float* x, int32_t M, int32_t d,
+                               int32_t K, const float* g_lo, const float* g_hi, int32_t split_row,
+                               const float* w2, const float* w2b, int32_t N2, const float* bias,
+                               int32_t block_n1, int32_t block_n2, float* x_out, float* y_out,
+                               void* stream) {
+  MSD_REQUIRE(a && w_out && x && g_lo && g_hi && w2 && x_out && y_out,
+              "msd_op_dense_deferred_norm: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool gated = w2b != nullptr;
+  const int Ng = gated ? 2 * N2 : N2;
+  TempBufs tb;
+  bf16 *ab = nullptr, *wo = nullptr, *opnd = nullptr, *w2p = nullptr, *yb = nullptr;
+  float* ss = nullptr;
+  int* step0 = nullptr;
+  const int bn1 = block_n1 ? block_n1 : gemm_pick_pair_bn(M, d);
+  MSD_REQUIRE(bn1 > 0 && d % bn1 == 0, "msd_op_dense_deferred_norm: block_n1 must divide d");
+  const int parts = d / bn1;
+  MSD_TRY(tb.get(&ab, static_cast<size_t>(M) * K));
+  MSD_TRY(tb.get(&wo, static_cast<size_t>(d) * K));
+  MSD_TRY(tb.get(&opnd, static_cast<size_t>(M) * d));
+  MSD_TRY(tb.get(&w2p, static_cast<size_t>(Ng) * d));
+  MSD_TRY(tb.get(&yb, static_cast<size_t>(M) * N2));
+  MSD_TRY(tb.get(&ss, static_cast<size_t>(parts) * M));
+  MSD_TRY(tb.get(&step0, 1));
+  MSD_CUDA_CHECK(cudaMemsetAsync(step0, 0, sizeof(int), st));
+  MSD_TRY(launch_f32_to_bf16(a, ab, static_cast<long long>(M) * K, st));
+  MSD_TRY(launch_pack_weight(w_out, K, d, wo, K, 0, 0, 0, st));
+  if (gated) MSD_TRY(launch_pack_gated(w2, w2b, d, N2, w2p, d, st));
+  else MSD_TRY(launch_pack_weight(w2, d, N2, w2p, d, 0, 0, 0, st));
+  MSD_CUDA_CHECK(cudaMemcpyAsync(x_out, x, static_cast<size_t>(M) * d * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+  GemmArgs g1;
+  memset(&g1, 0, sizeof(g1));
+  g1.A = ab; g1.B = wo; g1.M = M; g1.N = d; g1.K = K; g1.lda = K; g1.ldb = K;
+  g1.epilogue = EPI_RESID_PREP; g1.out = x_out; g1.ldo = d; g1.resid = x_out; g1.block_n = bn1;
+  g1.step = step0;
+  g1.prep.g_lo = g_lo; g1.prep.g_hi = g_hi; g1.prep.split_row = split_row;
+  g1.prep.a = opnd; g1.prep.lda = d; g1.prep.ss = ss; g1.prep.ss_stride = M;
+  MSD_TRY(launch_gemm(g1, st));
+  GemmArgs g2;
+  memset(&g2, 0, sizeof(g2));
+  g2.A = opnd; g2.B = w2p; g2.M = M; g2.N = Ng; g2.K = d; g2.lda = d; g2.ldb = d;
+  g2.epilogue = gated ? EPI_GATED_GELU : EPI_BF16; g2.out = yb; g2.ldo = N2; g2.block_n = block_n2;
+  g2.step = step0;
+  g2.rs.ss_lo = ss; g2.rs.ss_hi = ss; g2.rs.parts_lo = parts; g2.rs.parts_hi = parts;
+  g2.rs.split_row = M; g2.rs.ss_stride = M; g2.rs.inv_d = 1.0f / static_cast<float>(d);
+  g2.rs.col_bias = bias;
+  MSD_TRY(launch_gemm(g2, st));
+  MSD_TRY(launch_bf16_rows_to_f32(yb, N2, 0, y_out, M, N2, st));
   MSD_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }

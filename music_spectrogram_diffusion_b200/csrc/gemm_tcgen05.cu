@@ -48,6 +48,9 @@ struct GemmDev {
   // exit, then clock64 at: entry, set-up done (after the cluster sync), dependency wait returned
   // (epilogue warp), first accumulator ready, last chunk stored, exit
   long long* trace;
+  GemmPrep prep;       // EPI_RESID_PREP (DN instances only)
+  GemmRowScale rs;     // row scale + bias on EPI_BF16 / EPI_GATED_GELU (DN instances only)
+  const int* step;
 };
 
 template <int BN>
@@ -241,15 +244,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 //   warp 1 (one lane, leader)      MMA issuer; commits multicast to both CTAs' barriers
 //   warps 2..5 (both CTAs)         epilogue of the CTA's own 128 accumulator rows
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int DN = 0>
 struct PairCfg {
   static constexpr int HALF_N = BN / 2;
   static constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // epilogue staging: O ring 4 x [128 rows x 128 B] (source of the TMA stores / TMA reduce-adds;
-  // the bf16 path uses the first slot as 4 per-warp transpose tiles)
-  static constexpr int EPI_BYTES = 4 * 16384;
-  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES > 8 ? 8 : (160 * 1024) / STAGE_BYTES;
+  // the bf16 path uses the first slot as 4 per-warp transpose tiles).  The deferred-normalisation
+  // producer (DN == 2) adds an operand ring 4 x [128 rows x 64 B] behind it and pays with stages.
+  static constexpr int O_RING_BYTES = 4 * 16384;
+  // (+ 2 x BN floats: the tile's two column-gain rows, staged once per tile)
+  static constexpr int A_RING_BYTES = DN == 2 ? 4 * 8192 + 2 * BN * 4 : 0;
+  static constexpr int EPI_BYTES = O_RING_BYTES + A_RING_BYTES;
+  static constexpr int STAGE_BUDGET = DN == 2 ? (227 * 1024 - 1024 - 512 - EPI_BYTES) : 160 * 1024;
+  static constexpr int STAGES = STAGE_BUDGET / STAGE_BYTES > 8 ? 8 : STAGE_BUDGET / STAGE_BYTES;
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + EPI_BYTES + 512 /*barriers*/ + 1024 /*align*/;
   static constexpr uint32_t ACC_COLS = BN;  // columns per accumulator buffer
@@ -337,12 +345,42 @@ __device__ __forceinline__ void epilogue_bf16_rows(const GemmDev& p, uint8_t* ti
   __syncwarp();
 }
 
-template <int BN>
+// acc[0:32] = r, acc[32:64] = g:  acc = acc * inv_r + bias[0:64]
+__device__ __forceinline__ void scale_bias_64(uint32_t (&r)[32], uint32_t (&g)[32], float inv_r,
+                                              const float* bias) {
+  if (bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b0 = b4[q], b1 = b4[8 + q];  // staged in shared memory: broadcast reads
+      r[4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(r[4 * q + 0]), inv_r, b0.x));
+      r[4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * q + 1]), inv_r, b0.y));
+      r[4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * q + 2]), inv_r, b0.z));
+      r[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * q + 3]), inv_r, b0.w));
+      g[4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(g[4 * q + 0]), inv_r, b1.x));
+      g[4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(g[4 * q + 1]), inv_r, b1.y));
+      g[4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(g[4 * q + 2]), inv_r, b1.z));
+      g[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(g[4 * q + 3]), inv_r, b1.w));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      r[i] = __float_as_uint(__uint_as_float(r[i]) * inv_r);
+      g[i] = __float_as_uint(__uint_as_float(g[i]) * inv_r);
+    }
+  }
+}
+
+// DN: instances carrying the deferred-normalisation epilogues (kernels.h): 1 = consumer (row
+// scale + bias row, GemmRowScale), 2 = producer (EPI_RESID_PREP, GemmPrep; tmap_aux = the bf16
+// operand it writes).  The plain instances (0) stay free of that code.
+template <int BN, int DN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               const __grid_constant__ CUtensorMap tmap_b,
-                              const __grid_constant__ CUtensorMap tmap_out, const GemmDev p) {
-  using Cfg = PairCfg<BN>;
+                              const __grid_constant__ CUtensorMap tmap_out,
+                              const __grid_constant__ CUtensorMap tmap_aux, const GemmDev p) {
+  using Cfg = PairCfg<BN, DN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -354,7 +392,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2] (leader's copy is the one used)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* xload_bar = tmem_empty_bar + 2;       // [4] residual chunk landed in its O-ring slot (DN 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xload_bar + 4);
+  uint8_t* sAring = sEpi + Cfg::O_RING_BYTES;     // [4][8 KB] (DN 2)
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -386,9 +426,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
     }
+    for (int a = 0; a < 4; ++a) mbar_init(&xload_bar[a], 1);
     fence_barrier_init();
   }
   if (warp == 2 && lane == 0 && !epi_is_bf16_out(p.epilogue)) tma_prefetch_desc(&tmap_out);
+  if (DN == 2 && warp == 3 && lane == 0) tma_prefetch_desc(&tmap_aux);
   if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before_sync();
   cluster_sync_all();
@@ -473,6 +515,66 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int tile_row = (tile % m_pairs) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
       const int row0 = tile_row + lg * 32;
       const int n0 = (tile / m_pairs) * BN;
+      // deferred normalisation, consumer side: this thread's row scale and the bias row
+      // (requested before the accumulator is awaited)
+      float inv_r = 1.0f;
+      const float* bias = nullptr;
+      if constexpr (DN == 1) {
+        if (p.rs.ss_lo != nullptr) {
+          const int grow = row0 + lane;
+          const bool lo = grow < p.rs.split_row;
+          const float* ssp = (lo ? p.rs.ss_lo : p.rs.ss_hi) + grow;
+          const int parts = lo ? p.rs.parts_lo : p.rs.parts_hi;
+          float ss = 0.f;
+          if (grow < p.M)
+            for (int t = 0; t < parts; ++t) ss += ssp[static_cast<size_t>(t) * p.rs.ss_stride];
+          inv_r = rsqrtf(ss * p.rs.inv_d + 1e-6f);
+          if (p.rs.col_bias != nullptr) {
+            // the tile's bias row goes to shared memory once (slots 1.. of the O ring are unused by
+            // the bf16 epilogues), double-buffered over tiles: a warp that runs ahead by one tile
+            // must not overwrite what a slower warp still reads
+            float* sb = reinterpret_cast<float*>(sEpi + 16384) + (tcount & 1) * BN;
+            const int e = static_cast<int>(threadIdx.x) - 64;
+            if (e < BN / 4)
+              reinterpret_cast<float4*>(sb)[e] = __ldg(reinterpret_cast<const float4*>(
+                  p.rs.col_bias + static_cast<long long>(*p.step) * p.rs.bias_step_stride + n0) + e);
+            named_barrier_sync_c<1>(128);
+            bias = sb;
+          }
+        }
+      }
+      // deferred normalisation, producer side: the residual chunks are TMA-loaded into the O-ring
+      // slots they will be stored from (the first four before the accumulator is awaited)
+      bool prep = false;
+      const float* gvec = nullptr;
+      if constexpr (DN == 2) {
+        prep = p.epilogue == EPI_RESID_PREP && tile_row < p.M;
+        if (prep) {
+          if (epi_leader) {
+            if (tcount > 0) tma_store_wait_read<0>();  // the previous tile's stores have left the ring
+            for (int c = 0; c < (NCH < 4 ? NCH : 4); ++c) {
+              const uint32_t slot = (gc + c) & 3;
+              mbar_arrive_expect_tx(&xload_bar[slot], 16384);
+              tma_load_2d(sO + slot * 16384, &tmap_out, &xload_bar[slot], n0 + c * 32, tile_row);
+            }
+          }
+          // the tile's two column-gain rows (rows below / from split_row) go to shared memory once
+          float* sg = reinterpret_cast<float*>(sAring + 4 * 8192);
+          {
+            const long long st = *p.step;
+            const int e = static_cast<int>(threadIdx.x) - 64;
+            const int which = e / (BN / 4), idx = e - which * (BN / 4);
+            if (which < 2) {
+              const float* src = which == 0 ? p.prep.g_lo + st * p.prep.g_lo_step_stride
+                                            : p.prep.g_hi + st * p.prep.g_hi_step_stride;
+              reinterpret_cast<float4*>(sg + which * BN)[idx] =
+                  __ldg(reinterpret_cast<const float4*>(src + n0) + idx);
+            }
+          }
+          gvec = sg + (row0 + lane < p.prep.split_row ? 0 : BN);
+          named_barrier_sync_c<1>(128);  // gains staged (their last readers passed the previous tile's barriers)
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
       if (trc && tcount == 0) trc[6] = clock64();
@@ -485,6 +587,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_32x32b_x32(t_row + c, r);
           tmem_ld_32x32b_x32(t_row + c + 32, g);
           tmem_ld_wait();
+          if constexpr (DN == 1) {
+            if (p.rs.ss_lo != nullptr) scale_bias_64(r, g, inv_r, bias ? bias + c : nullptr);
+          }
           uint4 ch[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -532,6 +637,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_32x32b_x32(t_row + c, r);
           tmem_ld_32x32b_x32(t_row + c + 32, g);
           tmem_ld_wait();
+          if constexpr (DN == 1) {
+            if (p.rs.ss_lo != nullptr) scale_bias_64(r, g, inv_r, bias ? bias + c : nullptr);
+          }
           uint4 ch[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -556,8 +664,12 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // the store of chunk c - 4 must have read its slot before chunk c overwrites it.
         const int trow = lg * 32 + lane;   // row inside the CTA's 128-row tile
         const int grow = tile_row + trow;  // global row
+        float ssum = 0.f;
+        // (DN 2: a CTA whose rows are padding loads and stores nothing: skip its chunks, so that
+        // the slot / barrier phase counter gc only counts chunks that were really loaded)
+        const int nch_run = (DN == 2 && !prep) ? 0 : NCH;
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++gc) {
+        for (int c = 0; c < nch_run; ++c, ++gc) {
           const uint32_t slot = gc & 3;
           tmem_ld_32x32b_x32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -579,6 +691,30 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
               v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
             }
           }
+          if constexpr (DN == 2) {
+            if (prep) {
+              // v = acc + residual chunk (landed in this chunk's slot); operand chunk = bf16(v * g)
+              mbar_wait(&xload_bar[slot], (gc >> 2) & 1u);
+              const uint8_t* xr = sO + slot * 16384 + trow * 128;
+              const float4* g4 = reinterpret_cast<const float4*>(gvec + c * 32);
+              uint8_t* arow = sAring + slot * 8192 + trow * 64;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 xa = *reinterpret_cast<const float4*>(xr + (((2 * q) ^ (trow & 7)) * 16));
+                const float4 xb = *reinterpret_cast<const float4*>(xr + (((2 * q + 1) ^ (trow & 7)) * 16));
+                const float4 ga = g4[2 * q], gb = g4[2 * q + 1];
+                float* w = v + 8 * q;
+                w[0] += xa.x; w[1] += xa.y; w[2] += xa.z; w[3] += xa.w;
+                w[4] += xb.x; w[5] += xb.y; w[6] += xb.z; w[7] += xb.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ssum = fmaf(w[i], w[i], ssum);
+                // SWIZZLE_64B: 16-byte unit index ^= bits 7..8 of the tile offset = (row >> 1) & 3
+                *reinterpret_cast<uint4*>(arow + ((q ^ ((trow >> 1) & 3)) * 16)) =
+                    make_uint4(pack_bf16(w[0] * ga.x, w[1] * ga.y), pack_bf16(w[2] * ga.z, w[3] * ga.w),
+                               pack_bf16(w[4] * gb.x, w[5] * gb.y), pack_bf16(w[6] * gb.z, w[7] * gb.w));
+              }
+            }
+          }
           uint8_t* orow = sO + slot * 16384 + trow * 128;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -587,11 +723,15 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           fence_proxy_async_smem();
           // after this barrier everyone may write the NEXT chunk's slot: its previous user is the
           // store issued three chunks ago, so at most the two newest groups may still be reading
-          if (epi_leader) tma_store_wait_read<2>();
+          // (DN 2: a slot is rewritten only by a residual load issued after wait_read<0> below)
+          if (DN != 2 && epi_leader) tma_store_wait_read<2>();
           named_barrier_sync_c<1>(128);
           if (epi_leader) {
             if (tile_row < p.M) {  // M % 128 == 0: a CTA's rows are all valid or all padding
-              if (has_res) {
+              if (DN == 2 && prep) {
+                tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row);
+                tma_store_2d(&tmap_aux, sAring + slot * 8192, n0 + c * 32, tile_row);
+              } else if (has_res) {
                 tma_reduce_add_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row);
               } else {
                 tma_store_2d(&tmap_out, sO + slot * 16384, n0 + c * 32, tile_row);
@@ -600,7 +740,17 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             }
             tma_store_commit();
+            if constexpr (DN == 2) {
+              if (prep && c + 4 < NCH) {  // refill this slot with the residual chunk four ahead
+                tma_store_wait_read<0>();
+                mbar_arrive_expect_tx(&xload_bar[slot], 16384);
+                tma_load_2d(sO + slot * 16384, &tmap_out, &xload_bar[slot], n0 + (c + 4) * 32, tile_row);
+              }
+            }
           }
+        }
+        if constexpr (DN == 2) {
+          if (prep) p.prep.ss[static_cast<size_t>(n0 / BN) * p.prep.ss_stride + grow] = ssum;
         }
       }
       // accumulator drained: let the leader's MMA warp reuse it
@@ -639,10 +789,10 @@ static int gemm_sm_count() {
   return cached;
 }
 
-template <int BN>
+template <int BN, int DN = 0>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                const GemmDev& d, cudaStream_t st) {
-  using Cfg = PairCfg<BN>;
+                const CUtensorMap& taux, const GemmDev& d, cudaStream_t st) {
+  using Cfg = PairCfg<BN, DN>;
   const int m_pairs = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_tiles = m_pairs * (d.N / BN);
   const int sms = gemm_sm_count();
@@ -650,17 +800,24 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   ProfScope prof(KC_GEMM, 2.0 * d.M * d.N * d.K,
                  2.0 * (static_cast<double>(d.M) * d.K + static_cast<double>(d.N) * d.K) +
                      4.0 * d.M * d.N, st);
-  MSD_CUDA_CHECK(launch_kernel(gemm_bf16_tcgen05_pair_kernel<BN>, dim3(2 * clusters), dim3(192),
-                               Cfg::SMEM_BYTES, st, ta, tb, tout, d));
+  MSD_CUDA_CHECK(launch_kernel(gemm_bf16_tcgen05_pair_kernel<BN, DN>, dim3(2 * clusters), dim3(192),
+                               Cfg::SMEM_BYTES, st, ta, tb, tout, taux, d));
   ++g_launch_count;
   return 0;
 }
 
 template <int BN>
 int configure_pair() {
-  MSD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<BN>,
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<BN, 0>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      PairCfg<BN>::SMEM_BYTES));
+                                      PairCfg<BN, 0>::SMEM_BYTES));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<BN, 1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PairCfg<BN, 1>::SMEM_BYTES));
+  MSD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<BN, 2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PairCfg<BN, 2>::SMEM_BYTES));
+  static_assert(PairCfg<BN, 2>::SMEM_BYTES <= 227 * 1024 && PairCfg<BN, 2>::STAGES >= 3, "smem budget");
   return 0;
 }
 
@@ -768,6 +925,27 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.resid = a.resid; d.pos = a.pos; d.pos_rows = a.pos_rows > 0 ? a.pos_rows : 1;
   d.pos_shift = a.pos_shift; d.dup_rows = a.dup_rows;
   d.trace = a.trace;
+  d.prep = a.prep; d.rs = a.rs; d.step = a.step;
+  const bool dn = a.epilogue == EPI_RESID_PREP || a.rs.ss_lo != nullptr;
+  if (dn) {
+    MSD_REQUIRE(pair, "gemm: deferred normalisation exists in the CTA-pair kernel only");
+    if (a.epilogue == EPI_RESID_PREP) {
+      MSD_REQUIRE(a.resid != nullptr && a.resid == a.out, "gemm: EPI_RESID_PREP works in place (out == resid)");
+      MSD_REQUIRE(a.prep.a && a.prep.ss && a.prep.g_lo && a.prep.g_hi && a.prep.lda % 8 == 0 &&
+                      a.prep.ss_stride >= a.M,
+                  "gemm: EPI_RESID_PREP needs prep.a / ss / g_lo / g_hi (lda %% 8 == 0, ss_stride >= M)");
+      MSD_REQUIRE(a.step != nullptr || (a.prep.g_lo_step_stride == 0 && a.prep.g_hi_step_stride == 0),
+                  "gemm: step-dependent column scales need the device step index");
+    }
+    if (a.rs.ss_lo != nullptr) {
+      MSD_REQUIRE(a.epilogue == EPI_BF16 || a.epilogue == EPI_GATED_GELU,
+                  "gemm: the row scale applies to the bf16 and gated epilogues only");
+      MSD_REQUIRE(a.rs.ss_hi != nullptr && a.rs.parts_lo > 0 && a.rs.parts_hi > 0 && a.rs.inv_d > 0.f,
+                  "gemm: incomplete row-scale description");
+      MSD_REQUIRE(a.step != nullptr || a.rs.col_bias == nullptr || a.rs.bias_step_stride == 0,
+                  "gemm: a step-dependent bias row needs the device step index");
+    }
+  }
   if (pair) {
     CUtensorMap tout = ta;  // placeholder unless the epilogue is an fp32 one
     if (!epi_is_bf16_out(a.epilogue)) {
@@ -779,12 +957,32 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
                                          static_cast<size_t>(a.ldo) * 4, static_cast<size_t>(a.N) * 4,
                                          a.M, cudaMemcpyDeviceToDevice, stream));
     }
+    if (a.epilogue == EPI_RESID_PREP) {
+      CUtensorMap taux;
+      if (int rc = make_tmap_bf16_2d_half(&taux, a.prep.a, a.M, a.N, a.prep.lda, BLOCK_M)) return rc;
+      switch (bn) {
+        case 64: return launch_pair<64, 2>(ta, tb, tout, taux, d, stream);
+        case 96: return launch_pair<96, 2>(ta, tb, tout, taux, d, stream);
+        case 128: return launch_pair<128, 2>(ta, tb, tout, taux, d, stream);
+        case 192: return launch_pair<192, 2>(ta, tb, tout, taux, d, stream);
+        default: return launch_pair<256, 2>(ta, tb, tout, taux, d, stream);
+      }
+    }
+    if (dn) {
+      switch (bn) {
+        case 64: return launch_pair<64, 1>(ta, tb, tout, ta, d, stream);
+        case 96: return launch_pair<96, 1>(ta, tb, tout, ta, d, stream);
+        case 128: return launch_pair<128, 1>(ta, tb, tout, ta, d, stream);
+        case 192: return launch_pair<192, 1>(ta, tb, tout, ta, d, stream);
+        default: return launch_pair<256, 1>(ta, tb, tout, ta, d, stream);
+      }
+    }
     switch (bn) {
-      case 64: return launch_pair<64>(ta, tb, tout, d, stream);
-      case 96: return launch_pair<96>(ta, tb, tout, d, stream);
-      case 128: return launch_pair<128>(ta, tb, tout, d, stream);
-      case 192: return launch_pair<192>(ta, tb, tout, d, stream);
-      default: return launch_pair<256>(ta, tb, tout, d, stream);
+      case 64: return launch_pair<64>(ta, tb, tout, ta, d, stream);
+      case 96: return launch_pair<96>(ta, tb, tout, ta, d, stream);
+      case 128: return launch_pair<128>(ta, tb, tout, ta, d, stream);
+      case 192: return launch_pair<192>(ta, tb, tout, ta, d, stream);
+      default: return launch_pair<256>(ta, tb, tout, ta, d, stream);
     }
   }
   switch (bn) {

@@ -70,6 +70,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // Same for fp32 with box = [box_rows, 32 cols] (128-byte inner extent), SWIZZLE_128B.
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                      uint64_t ld, uint32_t box_rows);
+// bf16 with box = [box_rows, 32 cols] (64-byte inner extent), SWIZZLE_64B.
+int make_tmap_bf16_2d_half(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t ld, uint32_t box_rows);
 
 // ---------------------------------------------------------------------------
 // GEMM: D[M,N] = A[M,K] * B[N,K]^T, bf16 operands (both K-major), fp32 accumulate
@@ -85,6 +88,36 @@ enum GemmEpilogue : int {
   EPI_GATED_GELU_SPLIT3 = 5,  // fp32-accurate mode: g = gelu(acc[0:32]) * acc[32:64] with the exact
                               //   tanh, written as bf16 [M, 3 * N/2] = [hi(g) | lo(g) | hi(g)]
                               //   (the A operand of a 3 x bf16 split-precision GEMM); CTA-pair kernel
+  EPI_RESID_PREP = 6,  // deferred normalisation, producer side (CTA-pair kernel; out == resid):
+                       //   x = acc + resid (f32, in place); prep.a[r, :] = bf16(x[r, :] * g(r)[:])
+                       //   with g = prep.g_lo for r < prep.split_row else prep.g_hi; and
+                       //   prep.ss[tile_n, r] = sum over the tile's columns of x^2
+};
+
+// Deferred normalisation (bf16 mode): instead of a stand-alone rmsnorm (+FiLM)
+// kernel between a residual projection and the next projection,
+//   y = (rmsnorm(x) * gamma * (1 + fs) + fb) W   ==   inv_r[r] * ((x * g') W) + (fb W)
+// with g' = gamma (1 + fs) per column and inv_r = rsqrt(mean(x^2) + eps) per row.  The residual
+// GEMM that produces x also writes the column-scaled bf16 operand and the row sums of squares
+// (GemmPrep); the consuming GEMM scales its accumulator rows and adds the bias row (GemmRowScale).
+// Vectors that depend on the diffusion step are addressed as base + (*step) * step_stride.
+struct GemmPrep {
+  const float* g_lo;        // [N] column scale for rows < split_row
+  const float* g_hi;        // [N] column scale for rows >= split_row (may equal g_lo)
+  long long g_lo_step_stride, g_hi_step_stride;
+  int split_row;
+  bf16* a;                  // [M, lda] scaled operand of the next GEMM
+  int lda;
+  float* ss;                // [N / block_n, ss_stride] partial row sums of squares
+  int ss_stride;
+};
+struct GemmRowScale {
+  const float* ss_lo;       // partial sums for rows < split_row: ss_lo[t * ss_stride + r], t < parts_lo
+  const float* ss_hi;       // same for rows >= split_row
+  int parts_lo, parts_hi, split_row, ss_stride;
+  float inv_d;              // 1 / (normalised width)
+  const float* col_bias;    // [N] added after the row scale, or null
+  long long bias_step_stride;
 };
 
 struct GemmArgs {
@@ -106,6 +139,11 @@ struct GemmArgs {
   int block_n;           // 0 = auto
   int variant;           // 0 = CTA-pair persistent kernel (default), 1 = single-CTA kernel
   long long* trace;      // debugging: per-CTA stamps of the CTA-pair kernel (8 int64 per CTA), or null
+  // deferred normalisation (CTA-pair kernel): prep.a != null with EPI_RESID_PREP; rs.ss_lo != null
+  // with EPI_BF16 / EPI_GATED_GELU; `step` is the device step index the strides multiply
+  GemmPrep prep;
+  GemmRowScale rs;
+  const int* step;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 int gemm_configure();  // opt in to the kernels' dynamic shared memory sizes (idempotent)
@@ -202,6 +240,9 @@ struct SamplerArgs {
   // prefetched into L2 here, so that the 24 norm kernels of the next step do not each wait for
   // HBM (the table is 147 MB, every row is read once per call)
   const float* film; long long film_step_floats;
+  // further per-step tables prefetched the same way (deferred normalisation: column gains and the
+  // two bias-row tables), unused entries null
+  const float* pf[3]; long long pf_step_floats[3];
   // Classifier-free guidance split over two GPUs (BASELINE config 5): this GPU ran
   // ONE of the two decoder passes (xrole 1: the conditional one, 2: the unconditional one) and
   // `eps` holds its n values.  The kernel stores them into the peer GPU's exchange buffer with
@@ -271,6 +312,15 @@ int launch_pack_weight(const float* W, int K, int N, bf16* dst, int ldd, int n_o
 // receive part 0 (bf16(w)) or part 1 (bf16(w - bf16(w))).
 int launch_pack_gated(const float* W0, const float* W1, int K, int F, bf16* dst, int ldd,
                       cudaStream_t stream, int k_off = 0, int part = 0);
+// Deferred normalisation (GemmPrep / GemmRowScale): the operand + row sums of a residual stream
+// that no GEMM epilogue produced (first layer): a_out = bf16(x * g), ss_out[row] = sum x^2
+int launch_prep_rows(const float* x, const float* g, long long g_step_stride, const int* step, int rows,
+                     int d, bf16* a_out, int lda, float* ss_out, cudaStream_t stream);
+// load-time tables: out[s, :] = gamma * (1 + film[s, :]);  out[s, n] = sum_k fb[s, k] * W[n, k]
+int launch_film_gain(const float* film, long long film_stride, const float* gamma, float* out,
+                     long long out_stride, int steps, int d, cudaStream_t stream);
+int launch_film_bias(const float* fb, long long fb_stride, const bf16* W, int ldw, float* out,
+                     long long out_stride, int steps, int N, int K, cudaStream_t stream);
 // C[M,N] = act(A[M,K] * B[K,N]) fp32 SIMT (act: 0 none, 1 swish)
 int launch_sgemm_f32(const float* A, const float* B, float* C, int ldc, int M, int N, int K,
                      int act, cudaStream_t stream);

@@ -277,6 +277,27 @@ def op_dense_epilogue(a: torch.Tensor, w: torch.Tensor, epilogue: str, block_n: 
   return out
 
 
+def op_dense_deferred_norm(a: torch.Tensor, w_out: torch.Tensor, x: torch.Tensor, g_lo: torch.Tensor,
+                           g_hi: torch.Tensor, split_row: int, w2: torch.Tensor,
+                           w2b: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                           block_n1: int = 0, block_n2: int = 0):
+  """Residual projection with the deferred-normalisation epilogue + the projection consuming it
+  (msd_op_dense_deferred_norm): returns (x_out [M, d], y [M, N2])."""
+  lib = _native.load()
+  m, k = a.shape
+  d = w_out.shape[1]
+  n2 = w2.shape[1]
+  x_out = torch.empty(m, d, dtype=torch.float32, device=a.device)
+  y = torch.empty(m, n2, dtype=torch.float32, device=a.device)
+  keep = [t.contiguous() if t is not None else None for t in (a, w_out, x, g_lo, g_hi, w2, w2b, bias)]
+  _native.check(lib.msd_op_dense_deferred_norm(_ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), m, d, k,
+                                               _ptr(keep[3]), _ptr(keep[4]), split_row, _ptr(keep[5]),
+                                               _ptr(keep[6]), n2, _ptr(keep[7]), block_n1, block_n2,
+                                               _ptr(x_out), _ptr(y), _stream(a.device)),
+                'msd_op_dense_deferred_norm')
+  return x_out, y
+
+
 def op_attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
                      key_mask: Optional[torch.Tensor], heads: int) -> torch.Tensor:
   lib = _native.load()

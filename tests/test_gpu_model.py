@@ -265,6 +265,37 @@ def test_owner_merge_inside_the_step_graph(cuda_device, monkeypatch):
     assert (err > 0.1).float().mean().item() < 1e-2, other
 
 
+@pytest.mark.parametrize('style', ['concat_encodings', 'sum_cross_attends'])
+def test_deferred_normalisation_agrees_with_the_rmsnorm_kernels(cuda_device, monkeypatch, style):
+  """bf16 mode folds every pre-norm (+FiLM) of the decoder layers into the GEMM epilogues either
+  side of it; MSD_FUSED_NORM=0 keeps the stand-alone rmsnorm kernels.  Same
+  math, different rounding points: the two must agree far inside the oracle tolerance, for both
+  guidance passes (B = 3: the conditional rows end inside a 256-row tile) and both cross styles."""
+  t5 = config.t5_small()
+  t5.decoder_cross_attend_style = style
+  Ts, Ns, Cs, B, steps = 256, 256, 256, 3, 8
+  params = weights.synthetic_params(t5, Ts, Ns, Cs, seed=4)
+  toks, ctx, cmask = H.make_batch(B, Ts, Cs, seed=5, pad_second=True)
+  b = H.torch_batch(toks, ctx, cmask, cuda_device)
+  z = torch.randn(B, Ns, 128, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(1))
+  outs = {}
+  for mode in ('0', '1'):
+    monkeypatch.setenv('MSD_FUSED_NORM', mode)
+    eng = H.build_engine(t5, Ts, Ns, Cs, B, steps, 2.0, params)
+    eng.encode(b['encoder_input_tokens'], b['encoder_continuous_inputs'],
+               b['encoder_continuous_mask'])
+    first, second = eng.sample(seed=3).clone(), eng.sample(seed=3).clone()
+    assert torch.equal(first, second), mode
+    outs[mode] = (eng.decode_eps(z, 5, True).clone(), eng.decode_eps(z, 5, False).clone(), first)
+    eng.close()
+  for got, want in zip(outs['1'][:2], outs['0'][:2]):
+    rel = ((got - want).abs().mean() / want.abs().mean()).item()
+    assert rel < 1e-2, rel
+  span = 4.0 - np.log(1e-5)
+  err = (outs['1'][2] - outs['0'][2]).abs() / span * 2.0
+  assert err.mean().item() < 1e-2 and (err > 0.1).float().mean().item() < 1e-2
+
+
 def test_jax_random_stream_on_device_matches_numpy(cuda_device):
   """rng_kind = 1: the sampler's noise is jax.random.normal of PRNGKey(seed) / fold_in(key, i)
   (inference.py:203; diffusion_utils.py:389-390, 462).  Device draw vs jax_rng.py (numpy), which

@@ -70,6 +70,73 @@ def test_dot_product_attention_tail_split(cuda_device, monkeypatch, nb, heads, L
 
 
 @pytest.mark.parametrize('bkv,merge', [(64, 1), (64, 0), (128, 1), (128, 0)])
+def _pack_gated_cols(b0, b1):
+  """Accumulator column order of the gated projection: 32 columns of wi_0, 32 of wi_1, ..."""
+  F = b0.shape[-1]
+  return torch.stack([b0.view(F // 32, 32), b1.view(F // 32, 32)], dim=1).reshape(2 * F)
+
+
+@pytest.mark.parametrize('gated', [False, True])
+@pytest.mark.parametrize('M,d,K,N2,split_row,bn1,bn2', [
+    (4096, 768, 768, 2304, 2048, 0, 0),      # self-attention projection -> QKV of the B = 8 step
+    (4096, 768, 2048, 2048, 4096, 192, 256),  # wo -> next layer (explicit widths)
+    (512, 768, 768, 768, 256, 64, 64),        # batch 1: 12 column tiles of partial row sums
+    (4096, 768, 768, 768, 4096, 64, 0),       # 192 tiles on 74 CTA pairs: several tiles per CTA
+    (1280, 768, 512, 768, 600, 256, 0),       # 8 chunks per tile (ring refills), ragged split row
+    (384, 512, 512, 1024, 128, 128, 0),       # odd number of 128-row blocks, other width
+    (256, 256, 128, 256, 0, 256, 128)])       # one column tile, every row in the "hi" group
+def test_deferred_normalisation_pair(cuda_device, M, d, K, N2, split_row, bn1, bn2, gated):
+  """EPI_RESID_PREP + the row-scale / bias-row epilogues (kernels.h GemmPrep / GemmRowScale): the
+  pre-norm (+FiLM) of layers.py:632-666 split into a column gain where x is produced and a row
+  scale where the next accumulator is drained.  Checked (a) tightly against the same split written
+  in fp64 and (b) against the plain formulation norm -> FiLM -> dense of the oracle."""
+  from music_spectrogram_diffusion_b200 import engine
+  g = torch.Generator().manual_seed(M + d + K + N2 + gated)
+  a = bf16_round(torch.randn(M, K, generator=g))
+  w_out = bf16_round(torch.randn(K, d, generator=g) / np.sqrt(K))
+  x = torch.randn(M, d, generator=g) * 3
+  x[5] *= 30.0                                   # one row with a very different scale
+  gamma = 1 + 0.1 * torch.randn(2, d, generator=g)
+  fs = 0.2 * torch.randn(2, d, generator=g)
+  fb = 0.2 * torch.randn(2, d, generator=g)
+  gain = gamma * (1 + fs)                        # rows < split_row use [0], the others [1]
+  w2 = bf16_round(torch.randn(d, N2, generator=g) / np.sqrt(d))
+  w2b = bf16_round(torch.randn(d, N2, generator=g) / np.sqrt(d)) if gated else None
+  sel = (torch.arange(M) >= split_row).long()
+  # the bias row is one vector for the whole call: use group 0's FiLM bias for every row
+  bias0 = fb[0].double() @ w2.double()
+  bias1 = fb[0].double() @ w2b.double() if gated else None
+  bias = (_pack_gated_cols(bias0, bias1) if gated else bias0).float()
+  dev = cuda_device
+  x_out, y = engine.op_dense_deferred_norm(
+      a.to(dev), w_out.to(dev), x.to(dev), gain[0].to(dev), gain[1].to(dev), split_row, w2.to(dev),
+      None if w2b is None else w2b.to(dev), bias.to(dev), bn1, bn2)
+  x_out, y = x_out.cpu(), y.cpu()
+  # stage 1: the residual stream
+  xw = (x.double() + O.dense_general(a.double(), w_out.double()))
+  assert (x_out - xw.float()).abs().max().item() < 2e-4 * np.sqrt(K) * 4
+  # (a) the split formulation in fp64 from the device's own x_out
+  xo = x_out.double()
+  inv = torch.rsqrt((xo * xo).mean(-1, keepdim=True) + 1e-6)
+  opnd = bf16_round((xo * gain[sel].double()).float()).double()
+  u = inv * (opnd @ w2.double()) + bias0
+  if gated:
+    u1 = inv * (opnd @ w2b.double()) + bias1
+    want = (O.gelu_tanh(u) * u1).float()
+    tol = 2.0 ** -8 * want.abs() + 1.5e-3 * u1.abs().float() + 2e-3
+  else:
+    want = u.float()
+    tol = 2.0 ** -8 * want.abs() + 2e-3
+  err = (y - want).abs()
+  assert (err <= tol).all(), (err - tol).max().item()
+  # (b) the reference order of operations: rmsnorm * scale, FiLM, dense (fp64), bf16-level agreement
+  n = O.layer_norm(xw.float(), torch.ones(d)).double() * gain[sel].double() + fb[0].double()
+  r = n @ w2.double()
+  ref = (O.gelu_tanh(r) * (n @ w2b.double())).float() if gated else r.float()
+  rel = (y - ref).abs().mean().item() / ref.abs().mean().item()
+  assert rel < 1e-2, rel
+
+
 @pytest.mark.parametrize('splits', [0, 1, 3])
 @pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
     (1, 1, 128, 128, False), (2, 2, 128, 256, False), (2, 3, 256, 384, True),
