@@ -6,8 +6,10 @@ set -u
 mkdir -p gpurun_out
 TAG=${TAG:-r2}
 KREGEX='regex:gemm_bf16|attention_tcgen05|attention_combine|rmsnorm_film|sampler_step'
-# encode = 109 GEMM + 24 attention + 50 norm launches, then one warm-up step of 136 kernels
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 319 -c 136 --csv \
+# encode = 109 GEMM + 24 attention + 50 norm launches, then one warm-up step of 101 kernels
+# (deferred normalisation: 74 GEMM + 24 attention + 2 norm + sampler; 136 with MSD_FUSED_NORM=0)
+STEP_KERNELS=${STEP_KERNELS:-101}
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s $((183 + STEP_KERNELS)) -c $STEP_KERNELS --csv \
   --log-file gpurun_out/${TAG}_launches.csv python tools/profile_step.py > gpurun_out/${TAG}_prof_step.log 2>&1
 # cross-attention of layer 0 (128-key instance with the long/short split), self-attention (64-key
 # instance, two CTAs per SM), wi GEMM (gated GELU), self-out GEMM (TMA reduce-add epilogue)
