@@ -69,7 +69,6 @@ def test_dot_product_attention_tail_split(cuda_device, monkeypatch, nb, heads, L
     assert err < 3e-2, f'max err {err}'
 
 
-@pytest.mark.parametrize('bkv,merge', [(64, 1), (64, 0), (128, 1), (128, 0)])
 def _pack_gated_cols(b0, b1):
   """Accumulator column order of the gated projection: 32 columns of wi_0, 32 of wi_1, ..."""
   F = b0.shape[-1]
@@ -137,6 +136,7 @@ def test_deferred_normalisation_pair(cuda_device, M, d, K, N2, split_row, bn1, b
   assert rel < 1e-2, rel
 
 
+@pytest.mark.parametrize('bkv,merge', [(64, 1), (64, 0), (128, 1), (128, 0)])
 @pytest.mark.parametrize('splits', [0, 1, 3])
 @pytest.mark.parametrize('nb,heads,Lq,Lk,masked', [
     (1, 1, 128, 128, False), (2, 2, 128, 256, False), (2, 3, 256, 384, True),
