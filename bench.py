@@ -596,6 +596,11 @@ def run_ours(args):
         'avg_launch_us': 1e3 * g['ms'] / max(g['launches'], 1),
         'share_of_step': g['ms'] / total_ms if total_ms > 0 else None,
         'how': 'CUDA events around every launch of one uncaptured diffusion step (3 reps)',
+        # bf16 mode: the decoder layers' 36 pre-norms (+FiLM) run inside these launches' epilogues
+        # (deferred normalisation), so their time is GEMM time here while the
+        # FLOP count is the projections' alone; MSD_FUSED_NORM=0 gives the round-1 accounting
+        'includes': 'pre-norm + FiLM of the decoder layers (no stand-alone rmsnorm kernels)'
+                    if os.environ.get('MSD_FUSED_NORM', '1') != '0' and args.precision == 'bf16' else None,
     }
     step_tf = alg_flops_per_frame * (value / world) / 1e12
     line = {
